@@ -1,0 +1,124 @@
+"""Generate golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python oracle/make_golden.py            # writes tests/golden/*.pt and state_dict_keys.json
+
+Imports /root/reference/M3P/src/model/transformer.py (never copied), builds TransformerModel exactly
+as model/__init__.py:93 does, runs jointfwd / fwd / crossfwd / predict and the pretrain_under_step loss
+assembly (restated from xtrainer.py:2285-2375, because xtrainer itself needs apex) on seeded
+synthetic inputs with dropout = 0, and stores inputs, parameters, outputs, losses and gradients.
+The fixtures travel to the GPU box; /root/reference does not.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+REF = os.environ.get("M3P_REF", "/root/reference/M3P")
+
+from oracle import m3p_oracle as O  # noqa: E402
+
+
+def ref_params(emb_dim, n_layers, n_heads, n_words, n_langs=1, dropout=0.0):
+    langs = ["en", "fr", "de", "zh"][:n_langs]
+    return argparse.Namespace(
+        n_langs=n_langs, n_words=n_words, eos_index=2, pad_index=1,
+        id2lang={i: l for i, l in enumerate(langs)}, lang2id={l: i for i, l in enumerate(langs)},
+        emb_dim=emb_dim, n_heads=n_heads, n_layers=n_layers, n_dec_layers=n_layers,
+        dropout=dropout, attention_dropout=dropout, sinusoidal_embeddings=False, refine_layers=1,
+        attention_setting="v1", use_externel_att=False, gelu_activation=True, share_inout_emb=True, asm=False)
+
+
+def build_reference(p, seed=0):
+    sys.path.insert(0, REF)
+    from src.model.transformer import TransformerModel
+    torch.manual_seed(seed)
+    m = TransformerModel(p, is_encoder=True, with_output=True, is_crossModal=True)
+    # LayerNorm affine / biases away from their trivial init so the fixtures exercise them
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, t in m.named_parameters():
+            if "LayerNorm" in n or "layer_norm" in n:
+                t.add_(0.1 * torch.randn(t.shape, generator=g))
+    m.train()
+    return m
+
+
+def run_case(name, emb_dim, n_layers, n_heads, n_words, B, T, R, n_langs, ragged, seed):
+    p = ref_params(emb_dim, n_layers, n_heads, n_words, n_langs)
+    m = build_reference(p, seed)
+    sample_n = 2 if B % 4 else 4
+    batch = O.synthetic_batch(B, T, R, n_words, sample_n=sample_n, seed=seed + 100, ragged=ragged,
+                              n_mask_text=3, n_mask_img=2)
+    out = {"config": dict(emb_dim=emb_dim, n_layers=n_layers, n_heads=n_heads, n_words=n_words, n_langs=n_langs,
+                          B=B, T=T, R=R, sample_n=sample_n), "batch": batch}
+    x_img = batch["x_img"].clone().requires_grad_(True)
+
+    # ---- jointfwd + the four heads, loss assembly as xtrainer.py:2285-2375 ----
+    enc = m("jointfwd", x=batch["x"], lengths=batch["lengths"], x_img=x_img, lengths_img=batch["lengths_img"],
+            causal=False, langs=None, image_loc=batch["image_loc"], refine_image=False)
+    text_out = enc[R:]
+    img_out = enc[:R].transpose(0, 1)
+    y_text, pm_text = O.get_mask_(batch["x_labels"])
+    mlm_scores, mlm_loss = m("predict", tensor=text_out, pred_mask=pm_text, y=y_text, get_scores=False)
+    obj_scores, mrm_loss = m("predict", tensor=img_out, pred_mask=None, y=batch["obj_labels"].view(-1),
+                             get_scores=False, is_obj=True)
+    reg = m("predict", tensor=img_out, is_mrfr=True)
+    sel = batch["obj_labels"].reshape(-1) != -1
+    mrfr_loss = F.mse_loss(reg.reshape(-1, 2048)[sel], batch["ori_feats"].reshape(-1, 2048)[sel])
+    rel_scores = m("predict", tensor=enc.transpose(0, 1), is_relation=True)
+    ce = F.cross_entropy(rel_scores.view(-1, sample_n), batch["pos_labels"])
+    bce = F.binary_cross_entropy_with_logits(rel_scores.view(-1),
+                                             F.one_hot(batch["pos_labels"], sample_n).float().view(-1))
+    rel_loss = ce + bce
+    total = mlm_loss + mrm_loss + mrfr_loss + rel_loss
+    total.backward()
+    out["joint"] = dict(enc=enc.detach(), mlm_scores=mlm_scores.detach(), obj_scores=obj_scores.detach(),
+                        mrfr=reg.detach(), rel_scores=rel_scores.detach(),
+                        losses=dict(mlm=mlm_loss.item(), mrm=mrm_loss.item(), mrfr=mrfr_loss.item(),
+                                    rel=rel_loss.item(), total=total.item()),
+                        grad_x_img=x_img.grad.detach().clone())
+    grads = {n: t.grad.detach().clone() for n, t in m.named_parameters() if t.grad is not None}
+    out["joint"]["grads"] = grads
+    out["no_grad_params"] = sorted(n for n, t in m.named_parameters() if t.grad is None)
+    m.zero_grad()
+
+    # ---- text streams: fwd, crossfwd (with and without langs) ----
+    with torch.no_grad():
+        out["fwd_text"] = m("fwd", x=batch["x"], lengths=batch["lengths"], causal=False)
+        out["crossfwd_text"] = m("crossfwd", x=batch["x"], lengths=batch["lengths"], causal=False, stream_="text")
+        if n_langs > 1:
+            langs = torch.randint(0, n_langs, batch["x"].shape, generator=torch.Generator().manual_seed(seed))
+            out["langs"] = langs
+            out["crossfwd_text_langs"] = m("crossfwd", x=batch["x"], lengths=batch["lengths"], causal=False,
+                                           stream_="text", langs=langs)
+        out["fwd_image"] = m("fwd", x=batch["x_img"], lengths=batch["lengths_img"], causal=False, cross_modal=True,
+                             image_loc=batch["image_loc"])
+    sd = m.state_dict()
+    out["state_dict"] = {k: v.clone() for k, v in sd.items()
+                         if not k.startswith(("refine_embeddings", "cross_alignment", "encoder_attn", "layer_norm15",
+                                              "latent_transforms", "original_transforms",
+                                              "image_embeddings.image_distbution_embeddings",
+                                              "pred_layer.proj.weight"))}  # tied to embeddings.weight
+    keys = {k: list(v.shape) for k, v in sd.items()}
+    return out, keys
+
+
+if __name__ == "__main__":
+    gold = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(gold, exist_ok=True)
+    # C1 of BASELINE.json: 2 layers / 128 hidden, 16 text + 4 region tokens, batch 2
+    c1, keys = run_case("c1", 128, 2, 4, 1000, B=2, T=16, R=4, n_langs=1, ragged=False, seed=0)
+    torch.save(c1, os.path.join(gold, "c1_tiny.pt"))
+    # ragged lengths + several languages (cross_lang_embeddings) + odd sizes
+    c1r, keys_r = run_case("c1_ragged", 128, 2, 4, 600, B=4, T=12, R=5, n_langs=3, ragged=True, seed=7)
+    torch.save(c1r, os.path.join(gold, "c1_ragged_langs.pt"))
+    with open(os.path.join(gold, "state_dict_keys.json"), "w") as f:
+        json.dump({"c1_tiny": keys, "c1_ragged_langs": keys_r}, f, indent=0, sort_keys=True)
+    for n in ("c1_tiny.pt", "c1_ragged_langs.pt", "state_dict_keys.json"):
+        print(n, os.path.getsize(os.path.join(gold, n)))

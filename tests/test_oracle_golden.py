@@ -1,0 +1,97 @@
+"""Pin the CPU oracle (oracle/m3p_oracle.py) against outputs of the unmodified reference.
+
+The fixtures under tests/golden/ were produced by oracle/make_golden.py, which imports
+/root/reference/M3P/src/model/transformer.py.  Everything here runs on CPU in fp32.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import m3p_oracle as O
+
+CASES = ["c1_tiny.pt", "c1_ragged_langs.pt"]
+
+
+def _load(golden_dir, name):
+    g = torch.load(os.path.join(golden_dir, name), weights_only=False)
+    sd = dict(g["state_dict"])
+    sd["pred_layer.proj.weight"] = sd["embeddings.weight"]  # tied (transformer.py:728-729)
+    return g, sd
+
+
+def _close(a, b, tol=2e-5):
+    denom = b.norm().item() + 1e-12
+    return (a - b).norm().item() / denom < tol
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_jointfwd_heads_and_grads_match_reference(golden_dir, name):
+    g, sd = _load(golden_dir, name)
+    cfg, batch = g["config"], g["batch"]
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "pred_layer.proj.weight"}
+    leaf["pred_layer.proj.weight"] = leaf["embeddings.weight"]
+    b = dict(batch)
+    b["x_img"] = batch["x_img"].clone().requires_grad_(True)
+    enc, losses, total = O.pretrain_step_losses(leaf, cfg["n_layers"], cfg["n_heads"], b, cfg["sample_n"])
+    total.backward()
+    ref = g["joint"]
+    assert _close(enc.detach(), ref["enc"])
+    for k in ("mlm", "mrm", "mrfr", "rel"):
+        assert abs(losses[k].item() - ref["losses"][k]) < 1e-5 * max(1.0, abs(ref["losses"][k])), k
+    assert abs(total.item() - ref["losses"]["total"]) < 1e-5 * abs(ref["losses"]["total"])
+    assert _close(b["x_img"].grad, ref["grad_x_img"], 1e-4)
+    # padded rows of the encoder output are exactly zero (SURVEY appendix A invariants)
+    S = enc.shape[0]
+    mask = torch.arange(S)[:, None] < (batch["lengths"] + batch["lengths_img"])[None, :]
+    assert enc.detach()[~mask].abs().max().item() == 0.0 if (~mask).any() else True
+    n_checked = 0
+    for k, gref in ref["grads"].items():
+        if k == "pred_layer.proj.weight" or k not in leaf:
+            continue
+        got = leaf[k].grad
+        assert got is not None, k
+        assert _close(got, gref, 1e-4), k
+        n_checked += 1
+    assert n_checked > 40
+    # parameters the reference leaves without gradient on this path stay untouched here too
+    for k in g["no_grad_params"]:
+        if k in leaf:
+            assert leaf[k].grad is None, k
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_head_scores_match_reference(golden_dir, name):
+    g, sd = _load(golden_dir, name)
+    cfg, batch = g["config"], g["batch"]
+    R = cfg["R"]
+    enc = g["joint"]["enc"]
+    y_text, pm = O.get_mask_(batch["x_labels"])
+    scores, _ = O.predict_mlm(sd, enc[R:], pm, y_text)
+    assert _close(scores, g["joint"]["mlm_scores"])
+    oscores, _ = O.predict_obj(sd, enc[:R].transpose(0, 1), batch["obj_labels"].reshape(-1))
+    assert _close(oscores, g["joint"]["obj_scores"])
+    assert _close(O.predict_mrfr(sd, enc[:R].transpose(0, 1)), g["joint"]["mrfr"])
+    assert _close(O.predict_relation(sd, enc.transpose(0, 1)), g["joint"]["rel_scores"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_text_and_image_streams_match_reference(golden_dir, name):
+    g, sd = _load(golden_dir, name)
+    cfg, batch = g["config"], g["batch"]
+    L, H = cfg["n_layers"], cfg["n_heads"]
+    with torch.no_grad():
+        assert _close(O.fwd_text(sd, L, H, batch["x"], batch["lengths"]), g["fwd_text"])
+        assert _close(O.crossfwd_text(sd, L, H, batch["x"], batch["lengths"]), g["crossfwd_text"])
+        if "crossfwd_text_langs" in g:
+            got = O.crossfwd_text(sd, L, H, batch["x"], batch["lengths"], langs=g["langs"])
+            assert _close(got, g["crossfwd_text_langs"])
+            assert not _close(got, g["crossfwd_text"], 1e-3)  # langs matter for crossfwd, not for fwd
+        assert _close(O.fwd_image(sd, L, H, batch["x_img"], batch["lengths_img"], batch["image_loc"]), g["fwd_image"])
+
+
+def test_get_masks_matches_reference_semantics():
+    lengths = torch.tensor([3, 0, 5])
+    mask, attn = O.get_masks(5, lengths)
+    assert mask.tolist() == [[True] * 3 + [False] * 2, [False] * 5, [True] * 5]
+    assert attn is mask
