@@ -104,6 +104,153 @@ M3P_API int m3p_gemm_bf16(const m3p_gemm_args* args, m3p_stream_t stream);
 M3P_API int m3p_gemm_bf16_debug(const m3p_gemm_args* args, int32_t a_lbo, int32_t a_sbo, int32_t a_kstep,
                         int32_t b_lbo, int32_t b_sbo, int32_t b_kstep, m3p_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm (eps 1e-12, biased variance, affine) over the last dim of a bf16 [rows][d] tensor.
+ * Replaces layer_norm1 / layer_norm2 + the `tensor *= mask` that follows layer_norm2
+ * (transformer.py:953,957-958) and BertPredictionHeadTransform.LayerNorm (:605).
+ * Row mask: row = b*S + s is valid iff s < seqlen[b]; invalid rows are written as exact zeros.
+ * seqlen = NULL disables the mask.  mean/rstd [rows] are stashed for the backward.
+ * ------------------------------------------------------------------------------------------ */
+M3P_API int m3p_layernorm_fwd(const void* x, const float* gamma, const float* beta, const int32_t* seqlen,
+                              int64_t S, void* y, float* mean, float* rstd, int64_t rows, int64_t d, float eps,
+                              m3p_stream_t stream);
+
+/* Backward of LayerNorm, fused with the pieces that surround it on the path:
+ *   dy_eff  = rowmask * dropout_dy(dy)             dropout that FOLLOWED the LN (embeddings :266,943)
+ *   dx      = LN backward of dy_eff                (x, mean, rstd from the forward)
+ *   dx_drop = dropout_dx(dx)                       dropout that PRECEDED the residual add (:951, :226)
+ *   dgamma += sum dy_eff*xhat ; dbeta += sum dy_eff ; dbias += sum_rows dx_drop (bias of the linear
+ *   whose output fed the residual add).  Any of dx_drop / dgamma / dbeta / dbias may be NULL.
+ * dtype flags select fp32 (1) or bf16 (0) for x, dy, dx; supported: (0,0,0) (1,0,1) (1,1,0) (1,0,0). */
+typedef struct m3p_ln_bwd_args {
+  const void* dy;
+  const void* x;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  const int32_t* seqlen;
+  int64_t S;
+  void* dx;
+  void* dx_drop; /* bf16 */
+  float dx_drop_p;
+  uint64_t dx_seed;
+  float dy_drop_p;
+  uint64_t dy_seed;
+  float* dgamma;
+  float* dbeta;
+  float* dbias;
+  int64_t rows, d;
+  int32_t x_f32, dy_f32, dx_f32;
+} m3p_ln_bwd_args;
+M3P_API int m3p_layernorm_bwd(const m3p_ln_bwd_args* args, m3p_stream_t stream);
+
+/* out[j] += sum_rows x[row][j]   (bias gradients of q/k/v and lin1: autograd of :178-181,223) */
+M3P_API int m3p_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int64_t n, m3p_stream_t stream);
+
+/* out = bf16(scale * in): refreshes the bf16 tensor-core copies of the fp32 master parameters. */
+M3P_API int m3p_cast_f32_bf16(const float* in, void* out, int64_t n, float scale, m3p_stream_t stream);
+/* (A,B,F) fp32 -> (B,A,F) bf16: the reference's sequence-first inputs (x_img (R,bs,2048),
+ * transformer.py:895) to batch-major GEMM rows. */
+M3P_API int m3p_permute_cast_f32_bf16(const float* in, void* out, int64_t A, int64_t B, int64_t F,
+                                      m3p_stream_t stream);
+
+/* dst[i][:] = src[(f / n_inner) * stride_outer + (f % n_inner) * stride_inner ...], f = flat_idx[i]:
+ * the boolean-mask row gather of predict() (transformer.py:1206) on a strided (slen, bs, d) view.
+ * m3p_scatter_rows_bf16 is its adjoint for unique indices (dst pre-zeroed by the caller). */
+M3P_API int m3p_gather_rows_bf16(const void* src, const int64_t* flat_idx, int64_t n_inner, int64_t stride_outer,
+                                 int64_t stride_inner, void* dst, int64_t n, int64_t d, m3p_stream_t stream);
+M3P_API int m3p_scatter_rows_bf16(const void* src, const int64_t* flat_idx, int64_t n_inner, int64_t stride_outer,
+                                  int64_t stride_inner, void* dst, int64_t n, int64_t d, m3p_stream_t stream);
+
+/* F.cross_entropy(logits, y, reduction='mean', ignore_index) forward AND backward in one pass pair
+ * (transformer.py:112 MLM, :581 MRM): *loss = mean over non-ignored rows; dlogits = dloss/dlogits
+ * (bf16, same shape, pitch ldd); inv_count (device scalar) receives 1/#valid rows. */
+M3P_API int m3p_cross_entropy(const void* logits, int64_t ld, const int64_t* y, int64_t n, int64_t V,
+                              int64_t ignore_index, float* loss, float* inv_count, void* dlogits, int64_t ldd,
+                              m3p_stream_t stream);
+
+/* seq_relationship / seq_relationship2: Linear(d, 1) (transformer.py:713,716,1196,1200) and backward. */
+M3P_API int m3p_rowdot_fwd(const void* x, const float* w, const float* bias, float* out, int64_t rows, int64_t d,
+                           m3p_stream_t stream);
+M3P_API int m3p_rowdot_bwd(const float* dout, const void* x, const float* w, void* dx, float* dw, float* db,
+                           int64_t rows, int64_t d, m3p_stream_t stream);
+
+/* dst[idx[i]][:] += src[i][:] (fp32, atomic), rows with idx == skip_index skipped. */
+M3P_API int m3p_scatter_add_rows_f32(const float* src, const int64_t* idx, int64_t skip_index, float* dst, int64_t n,
+                                     int64_t d, m3p_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Embedding stage of jointfwd / fwd / crossfwd (transformer.py:897-943, 820-831, 1044-1062).
+ * Rows are batch-major, row = b*(R+T) + s, image rows first (s < R) as torch.cat at :929.
+ *   image row: e = e_img (x_img W_img^T + b_img, from m3p_gemm_bf16) + loc W_loc^T + b_loc ;
+ *              y = dropout(LN_img(e))                                         (:259-268)
+ *   text row : y = tok_emb[x] or text_embed                                    (:910-913)
+ *   then     : y += pos_emb[pos] (M3P_EMB_POS) ; += lang_emb[lang] (langs != NULL, text rows)
+ *              y *= mask (M3P_EMB_MASK_PRE, jointfwd order :940) ; y_pre = y
+ *              y = LN_emb(y) (M3P_EMB_LN) ; y = dropout(y) (M3P_EMB_DROP2) ;
+ *              y *= mask (M3P_EMB_MASK_POST, fwd/crossfwd order :831,1062) ; h0 = bf16(y)
+ * mask(b,s) = s < seqlen[b].  e_img is updated in place to the LN_img input (stash).
+ * ------------------------------------------------------------------------------------------ */
+enum { M3P_EMB_POS = 1, M3P_EMB_LN = 2, M3P_EMB_MASK_PRE = 4, M3P_EMB_MASK_POST = 8, M3P_EMB_DROP2 = 16 };
+
+typedef struct m3p_embed_args {
+  int64_t B, R, T, d;
+  int32_t flags;
+  float eps;
+  float drop_p;
+  uint64_t seed_img, seed_emb;
+  /* image stream */
+  float* e_img;           /* [B*R][d] fp32 in/out */
+  const float* image_loc; /* (R,B,5) fp32 */
+  const float* w_loc;     /* [d][5] */
+  const float* b_loc;     /* [d] */
+  const float* ln_img_g;
+  const float* ln_img_b;
+  float* img_mean;
+  float* img_rstd;
+  /* text stream */
+  const int64_t* x;        /* (T,B) token ids */
+  const float* tok_emb;    /* [V][d] fp32 */
+  const float* text_embed; /* optional [B][T][d] fp32 */
+  const int64_t* positions; /* optional (T,B) */
+  const float* pos_emb;
+  const int64_t* langs; /* optional (T,B) */
+  const float* lang_emb;
+  const int32_t* seqlen; /* [B] */
+  const float* ln_emb_g;
+  const float* ln_emb_b;
+  /* outputs */
+  float* y_pre; /* [B*S][d] fp32 (M3P_EMB_LN) */
+  float* emb_mean;
+  float* emb_rstd;
+  void* h0; /* [B*S][d] bf16 */
+} m3p_embed_args;
+M3P_API int m3p_embed_fwd(const m3p_embed_args* args, m3p_stream_t stream);
+
+/* Routing half of the embedding backward: dy_pre [B*S][d] fp32 (from m3p_layernorm_bwd on
+ * layer_norm_emb) is scattered to d_pos_emb / d_tok_emb (padding_idx skipped, :658) / d_lang_emb
+ * (+=, atomic) or copied to d_text_embed (FreeLB) and, for image rows, to dy_img [B*R][d] fp32. */
+typedef struct m3p_embed_bwd_args {
+  int64_t B, R, T, d;
+  int32_t flags;
+  const float* dy_pre;
+  const int32_t* seqlen;
+  const int64_t* x;
+  const int64_t* positions;
+  const int64_t* langs;
+  int64_t pad_index;
+  float* d_tok_emb;
+  float* d_text_embed;
+  float* d_pos_emb;
+  float* d_lang_emb;
+  float* dy_img;
+} m3p_embed_bwd_args;
+M3P_API int m3p_embed_bwd_route(const m3p_embed_bwd_args* args, m3p_stream_t stream);
+/* d w_loc[j][c] += sum_rows de[row][j] * image_loc[row][c] (autograd of :261, K = 5). */
+M3P_API int m3p_loc_wgrad(const void* de, const float* image_loc, float* dw_loc, int64_t B, int64_t R, int64_t d,
+                          m3p_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

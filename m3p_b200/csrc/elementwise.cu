@@ -1,0 +1,624 @@
+// HBM-bound kernels of the M3P path: LayerNorm forward/backward (with the residual-stream row mask
+// and the dropout of the preceding linear folded into the backward), bias-gradient column sums,
+// fp32->bf16 casts, gather / scatter of token rows, cross-entropy forward+backward, tiny linears.
+// One warp owns one row; 16-byte vector loads; warp-shuffle reductions; no shared-memory staging
+// (every element is touched once).  Grids are sized as multiples of the SM count.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace m3p {
+
+// ---- 8-wide vector access ---------------------------------------------------------------------
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* v) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  v[0] = bf16_lo(t.x); v[1] = bf16_hi(t.x); v[2] = bf16_lo(t.y); v[3] = bf16_hi(t.y);
+  v[4] = bf16_lo(t.z); v[5] = bf16_hi(t.z); v[6] = bf16_lo(t.w); v[7] = bf16_hi(t.w);
+}
+__device__ __forceinline__ void load8(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* v) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void store8(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+// 8 dropout keep-flags for elements [e0, e0+8), e0 even
+__device__ __forceinline__ void drop8(uint32_t e0, uint32_t seed_lo, uint32_t seed_hi, uint32_t thr16,
+                                      float scale, float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t h = drop_hash((e0 >> 1) + j, seed_lo, seed_hi);
+    v[2 * j] = ((h & 0xffffu) >= thr16) ? v[2 * j] * scale : 0.f;
+    v[2 * j + 1] = ((h >> 16) >= thr16) ? v[2 * j + 1] * scale : 0.f;
+  }
+}
+
+constexpr int EW_THREADS = 256;
+constexpr int EW_WARPS = EW_THREADS / 32;
+
+static int ew_grid(long long rows) {
+  long long need = (rows + EW_WARPS - 1) / EW_WARPS;
+  long long cap = (long long)sm_count() * 8;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+// =================================================================================================
+// LayerNorm forward:  y = mask * ((x - mean) * rstd * gamma + beta)      transformer.py:953,957-958
+// =================================================================================================
+template <int MAXC>
+__global__ void __launch_bounds__(EW_THREADS)
+ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+              const float* __restrict__ beta, const int32_t* __restrict__ seqlen, long long S,
+              __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+              long long rows, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * EW_WARPS;
+  const int nchunks = d >> 3;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    float v[MAXC][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
+        load8(x + row * d + ch * 8, v[c]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[c][j];
+      }
+    }
+    const float mean = warp_sum(sum) / d;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float t = v[c][j] - mean; sq += t * t; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / d + eps);
+    bool valid = true;
+    if (seqlen != nullptr) valid = (row % S) < seqlen[row / S];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
+        float g[8], b[8], o[8];
+        load8(gamma + ch * 8, g);
+        load8(beta + ch * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = valid ? fmaf((v[c][j] - mean) * rstd, g[j], b[j]) : 0.f;
+        store8(y + row * d + ch * 8, o);
+      }
+    }
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  }
+}
+
+// =================================================================================================
+// LayerNorm backward.
+//   dy_eff = mask * dropout_dy(dy)                 (dropout_dy: a dropout that followed the LN)
+//   xhat = (x - mean) * rstd ;  g = dy_eff * gamma
+//   dx = rstd * (g - mean_j(g) - xhat * mean_j(g * xhat))
+//   dgamma += sum_rows dy_eff * xhat ; dbeta += sum_rows dy_eff
+//   dx_drop = dropout_dx(dx)  (the dropout of the linear whose output fed this LN through the
+//             residual add: transformer.py:951,226) ; dbias += sum_rows dx_drop   (that linear's bias)
+// =================================================================================================
+struct LnBwdParams {
+  const void* dy; const void* x; const float* mean; const float* rstd; const float* gamma;
+  const int32_t* seqlen; long long S;
+  void* dx; __nv_bfloat16* dx_drop;
+  uint32_t dx_thr16, dx_seed_lo, dx_seed_hi; float dx_scale;
+  uint32_t dy_thr16, dy_seed_lo, dy_seed_hi; float dy_scale;
+  float* dgamma; float* dbeta; float* dbias;
+  long long rows; int d;
+};
+
+template <typename XT, typename DYT, typename DXT, int MAXC>
+__global__ void __launch_bounds__(EW_THREADS)
+ln_bwd_kernel(const LnBwdParams p) {
+  extern __shared__ float sacc[];  // [3][d]
+  const int d = p.d;
+  for (int i = threadIdx.x; i < 3 * d; i += EW_THREADS) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * EW_WARPS;
+  const int nchunks = d >> 3;
+  const XT* x = reinterpret_cast<const XT*>(p.x);
+  const DYT* dy = reinterpret_cast<const DYT*>(p.dy);
+  DXT* dx = reinterpret_cast<DXT*>(p.dx);
+
+  float acc_g[MAXC][8], acc_b[MAXC][8], acc_bias[MAXC][8];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc_g[c][j] = 0.f; acc_b[c][j] = 0.f; acc_bias[c][j] = 0.f; }
+
+  for (long long row = warp0; row < p.rows; row += nwarps) {
+    bool valid = true;
+    if (p.seqlen != nullptr) valid = (row % p.S) < p.seqlen[row / p.S];
+    const float mean = p.mean[row], rstd = p.rstd[row];
+    float xh[MAXC][8], g[MAXC][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
+        float xv[8], dv[8], gm[8];
+        load8(x + row * d + ch * 8, xv);
+        load8(dy + row * d + ch * 8, dv);
+        load8(p.gamma + ch * 8, gm);
+        if (p.dy_thr16 != 0)
+          drop8((uint32_t)row * (uint32_t)d + ch * 8, p.dy_seed_lo, p.dy_seed_hi, p.dy_thr16, p.dy_scale, dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dyv = valid ? dv[j] : 0.f;
+          xh[c][j] = (xv[j] - mean) * rstd;
+          g[c][j] = dyv * gm[j];
+          s1 += g[c][j];
+          s2 += g[c][j] * xh[c][j];
+          acc_g[c][j] += dyv * xh[c][j];
+          acc_b[c][j] += dyv;
+        }
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[c][j] - s1 - xh[c][j] * s2);
+        store8(dx + row * d + ch * 8, o);
+        if (p.dx_drop != nullptr) {
+          if (p.dx_thr16 != 0)
+            drop8((uint32_t)row * (uint32_t)d + ch * 8, p.dx_seed_lo, p.dx_seed_hi, p.dx_thr16, p.dx_scale, o);
+          store8(p.dx_drop + row * d + ch * 8, o);
+        }
+        if (p.dbias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // bias gradient sees the bf16-rounded value the GEMMs will consume
+            acc_bias[c][j] += o[j];
+          }
+        }
+      }
+    }
+  }
+  // block reduction through shared memory, then one global atomic per column per CTA
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sacc[ch * 8 + j], acc_g[c][j]);
+        atomicAdd(&sacc[d + ch * 8 + j], acc_b[c][j]);
+        if (p.dbias != nullptr) atomicAdd(&sacc[2 * d + ch * 8 + j], acc_bias[c][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += EW_THREADS) {
+    if (p.dgamma != nullptr) atomicAdd(p.dgamma + i, sacc[i]);
+    if (p.dbeta != nullptr) atomicAdd(p.dbeta + i, sacc[d + i]);
+    if (p.dbias != nullptr) atomicAdd(p.dbias + i, sacc[2 * d + i]);
+  }
+}
+
+template <typename XT, typename DYT, typename DXT>
+static int launch_ln_bwd(const LnBwdParams& p, cudaStream_t stream) {
+  const int grid = ew_grid(p.rows) < sm_count() * 2 ? ew_grid(p.rows) : sm_count() * 2;
+  const size_t smem = 3 * p.d * sizeof(float);
+  if (p.d <= 256) ln_bwd_kernel<XT, DYT, DXT, 1><<<grid, EW_THREADS, smem, stream>>>(p);
+  else if (p.d <= 768) ln_bwd_kernel<XT, DYT, DXT, 3><<<grid, EW_THREADS, smem, stream>>>(p);
+  else ln_bwd_kernel<XT, DYT, DXT, 4><<<grid, EW_THREADS, smem, stream>>>(p);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+// =================================================================================================
+// column sums (bias gradients): out[j] += sum_rows x[row][j]
+// =================================================================================================
+__global__ void __launch_bounds__(EW_THREADS)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, long long rows, int n,
+              long long rows_per_cta) {
+  // thread owns 8 consecutive columns of a 2048-column stripe; CTA walks its row range
+  const int col0 = (blockIdx.y * EW_THREADS + threadIdx.x) * 8;
+  if (col0 >= n) return;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long r = r0; r < r1; ++r) {
+    float v[8];
+    load8(x + r * ld + col0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(out + col0 + j, acc[j]);
+}
+
+// =================================================================================================
+// casts / permutes
+// =================================================================================================
+__global__ void __launch_bounds__(EW_THREADS)
+cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n8, float scale) {
+  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * EW_THREADS) {
+    float v[8];
+    load8(in + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= scale;
+    store8(out + i * 8, v);
+  }
+}
+// (A, B, F) fp32 -> (B, A, F) bf16     (seq-first reference inputs -> batch-major rows)
+__global__ void __launch_bounds__(EW_THREADS)
+permute_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int A, int B, int F8) {
+  const long long total = (long long)A * B * F8;
+  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < total;
+       i += (long long)gridDim.x * EW_THREADS) {
+    const int f = (int)(i % F8);
+    const long long ab = i / F8;
+    const int a = (int)(ab % A);
+    const int b = (int)(ab / A);  // output-major order: (b, a, f)
+    float v[8];
+    load8(in + (((long long)a * B + b) * F8 + f) * 8, v);
+    store8(out + i * 8, v);
+  }
+}
+
+// =================================================================================================
+// row gather / scatter (prediction heads, FreeLB input grads)
+//   gather : dst[i][:] = src[rows[i]][:]            (src addressed as base + row_t*stride_t + row_b*stride_b)
+// =================================================================================================
+__global__ void __launch_bounds__(EW_THREADS)
+gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int64_t* __restrict__ flat_idx, long long n_inner,
+                   long long stride_outer, long long stride_inner, __nv_bfloat16* __restrict__ dst, long long n, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * EW_WARPS;
+  for (long long i = warp0; i < n; i += nwarps) {
+    const long long f = flat_idx[i];
+    const __nv_bfloat16* s = src + (f / n_inner) * stride_outer + (f % n_inner) * stride_inner;
+    for (int ch = lane; ch < (d >> 3); ch += 32)
+      *reinterpret_cast<uint4*>(dst + i * d + ch * 8) = *reinterpret_cast<const uint4*>(s + ch * 8);
+  }
+}
+// scatter-add of bf16 rows into a (possibly strided) bf16 tensor is done by zero-fill + row copy
+// because masked positions are unique:  dst[rows[i]][:] = src[i][:]
+__global__ void __launch_bounds__(EW_THREADS)
+scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, const int64_t* __restrict__ flat_idx, long long n_inner,
+                    long long stride_outer, long long stride_inner, __nv_bfloat16* __restrict__ dst, long long n, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * EW_WARPS;
+  for (long long i = warp0; i < n; i += nwarps) {
+    const long long f = flat_idx[i];
+    __nv_bfloat16* t = dst + (f / n_inner) * stride_outer + (f % n_inner) * stride_inner;
+    for (int ch = lane; ch < (d >> 3); ch += 32)
+      *reinterpret_cast<uint4*>(t + ch * 8) = *reinterpret_cast<const uint4*>(src + i * d + ch * 8);
+  }
+}
+
+// =================================================================================================
+// cross-entropy forward + backward over bf16 logits (F.cross_entropy(reduction='mean', ignore_index))
+//   transformer.py:112 (MLM), :581 (MRM).  One CTA per row.
+//   loss += -(logit[y] - lse) / n_valid ;  dlogits = (softmax - onehot) / n_valid   (0 for ignored rows)
+// =================================================================================================
+__global__ void ce_count_kernel(const int64_t* __restrict__ y, long long n, long long ignore_index,
+                                float* __restrict__ inv_count) {
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) c += (y[i] != ignore_index) ? 1 : 0;
+  atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) *inv_count = s_cnt > 0 ? 1.0f / (float)s_cnt : 0.f;  // 0 valid rows: torch gives nan; we give 0 grads
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+ce_row_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const int64_t* __restrict__ y, int V,
+              long long ignore_index, const float* __restrict__ inv_count, float* __restrict__ loss,
+              __nv_bfloat16* __restrict__ dlogits, long long ldd) {
+  __shared__ float s_m[EW_WARPS], s_s[EW_WARPS];
+  const long long row = blockIdx.x;
+  const __nv_bfloat16* lp = logits + row * ld;
+  __nv_bfloat16* dp = dlogits + row * ldd;
+  const long long target = y[row];
+  const int nvec = V >> 3;
+  if (target == ignore_index) {
+    for (int i = threadIdx.x; i < nvec; i += EW_THREADS) *reinterpret_cast<uint4*>(dp + i * 8) = make_uint4(0, 0, 0, 0);
+    for (int i = nvec * 8 + threadIdx.x; i < V; i += EW_THREADS) dp[i] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  // pass 1: online max / sum(exp)
+  float m = -INFINITY, s = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += EW_THREADS) {
+    float v[8];
+    load8(lp + i * 8, v);
+    float mx = v[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) mx = fmaxf(mx, v[j]);
+    if (mx > m) { s *= __expf(m - mx); m = mx; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += __expf(v[j] - m);
+  }
+  for (int i = nvec * 8 + threadIdx.x; i < V; i += EW_THREADS) {
+    const float v = __bfloat162float(lp[i]);
+    if (v > m) { s *= __expf(m - v); m = v; }
+    s += __expf(v - m);
+  }
+  // warp then block combine of (m, s)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, m2);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+    m = mn;
+  }
+  if ((threadIdx.x & 31) == 0) { s_m[threadIdx.x >> 5] = m; s_s[threadIdx.x >> 5] = s; }
+  __syncthreads();
+  m = s_m[0]; s = s_s[0];
+#pragma unroll
+  for (int w = 1; w < EW_WARPS; ++w) {
+    const float m2 = s_m[w], s2 = s_s[w];
+    const float mn = fmaxf(m, m2);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+    m = mn;
+  }
+  const float lse = m + __logf(s);
+  const float inv_n = *inv_count;
+  if (threadIdx.x == 0) atomicAdd(loss, (lse - __bfloat162float(lp[target])) * inv_n);
+  // pass 2: gradient
+  const float inv_s = 1.0f / s;
+  for (int i = threadIdx.x; i < nvec; i += EW_THREADS) {
+    float v[8];
+    load8(lp + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float pj = __expf(v[j] - m) * inv_s;
+      if (i * 8 + j == target) pj -= 1.0f;
+      v[j] = pj * inv_n;
+    }
+    store8(dp + i * 8, v);
+  }
+  for (int i = nvec * 8 + threadIdx.x; i < V; i += EW_THREADS) {
+    float pj = __expf(__bfloat162float(lp[i]) - m) * inv_s;
+    if (i == target) pj -= 1.0f;
+    dp[i] = __float2bfloat16_rn(pj * inv_n);
+  }
+}
+
+// =================================================================================================
+// tiny linear d -> 1 (seq_relationship, transformer.py:713,1196) and its backward
+// =================================================================================================
+__global__ void __launch_bounds__(EW_THREADS)
+rowdot_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ out, long long rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float acc = 0.f;
+  for (int j = lane; j < d; j += 32) acc += __bfloat162float(x[row * d + j]) * w[j];
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc + bias[0];
+}
+// dx[row][j] = dout[row] * w[j] ; dw[j] += sum_rows dout[row] * x[row][j] ; db += sum dout
+__global__ void __launch_bounds__(EW_THREADS)
+rowdot_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                  __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long long rows, int d) {
+  const int j = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (j >= d) return;
+  float acc = 0.f, accb = 0.f;
+  const float wj = w[j];
+  for (long long r = 0; r < rows; ++r) {
+    const float g = dout[r];
+    acc += g * __bfloat162float(x[r * d + j]);
+    accb += g;
+    dx[r * d + j] = __float2bfloat16_rn(g * wj);
+  }
+  atomicAdd(dw + j, acc);
+  if (j == 0) atomicAdd(db, accb);
+}
+
+// bf16 -> fp32 elementwise add into (embedding-style) fp32 rows:  dst[idx[i]][:] += src[i][:]
+__global__ void __launch_bounds__(EW_THREADS)
+scatter_add_rows_f32_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, long long skip_index,
+                            float* __restrict__ dst, long long n, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * EW_WARPS;
+  for (long long i = warp0; i < n; i += nwarps) {
+    const long long r = idx[i];
+    if (r == skip_index) continue;
+    for (int c = lane; c < (d >> 2); c += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(src + i * d + c * 4);
+      atomicAdd(reinterpret_cast<float4*>(dst + r * d + c * 4), v);
+    }
+  }
+}
+
+}  // namespace m3p
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace m3p;
+
+extern "C" int m3p_layernorm_fwd(const void* x, const float* gamma, const float* beta, const int32_t* seqlen,
+                                 int64_t S, void* y, float* mean, float* rstd, int64_t rows, int64_t d, float eps,
+                                 m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(x && gamma && beta && y && mean && rstd, "m3p_layernorm_fwd: null pointer");
+  M3P_REQUIRE(rows > 0 && d > 0 && d % 8 == 0 && d <= 2048, "m3p_layernorm_fwd: d=%lld must be a multiple of 8, <= 2048",
+              (long long)d);
+  M3P_REQUIRE(seqlen == nullptr || S > 0, "m3p_layernorm_fwd: S must be > 0 with a row mask");
+  const int grid = ew_grid(rows);
+  auto X = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto Y = reinterpret_cast<__nv_bfloat16*>(y);
+  if (d <= 256) ln_fwd_kernel<1><<<grid, EW_THREADS, 0, stream>>>(X, gamma, beta, seqlen, S, Y, mean, rstd, rows, (int)d, eps);
+  else if (d <= 768) ln_fwd_kernel<3><<<grid, EW_THREADS, 0, stream>>>(X, gamma, beta, seqlen, S, Y, mean, rstd, rows, (int)d, eps);
+  else if (d <= 1024) ln_fwd_kernel<4><<<grid, EW_THREADS, 0, stream>>>(X, gamma, beta, seqlen, S, Y, mean, rstd, rows, (int)d, eps);
+  else ln_fwd_kernel<8><<<grid, EW_THREADS, 0, stream>>>(X, gamma, beta, seqlen, S, Y, mean, rstd, rows, (int)d, eps);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_layernorm_bwd(const m3p_ln_bwd_args* a, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(a && a->dy && a->x && a->mean && a->rstd && a->gamma && a->dx, "m3p_layernorm_bwd: null pointer");
+  M3P_REQUIRE(a->rows > 0 && a->d > 0 && a->d % 8 == 0 && a->d <= 1024,
+              "m3p_layernorm_bwd: d=%lld must be a multiple of 8, <= 1024", (long long)a->d);
+  M3P_REQUIRE(a->seqlen == nullptr || a->S > 0, "m3p_layernorm_bwd: S must be > 0 with a row mask");
+  M3P_REQUIRE(a->dx_drop_p >= 0.f && a->dx_drop_p < 1.f && a->dy_drop_p >= 0.f && a->dy_drop_p < 1.f,
+              "m3p_layernorm_bwd: dropout probability out of range");
+  LnBwdParams p{};
+  p.dy = a->dy; p.x = a->x; p.mean = a->mean; p.rstd = a->rstd; p.gamma = a->gamma;
+  p.seqlen = a->seqlen; p.S = a->S;
+  p.dx = a->dx; p.dx_drop = reinterpret_cast<__nv_bfloat16*>(a->dx_drop);
+  p.dx_thr16 = a->dx_drop_p > 0.f ? drop_thr16(a->dx_drop_p) : 0;
+  p.dx_scale = 1.0f / (1.0f - a->dx_drop_p);
+  p.dx_seed_lo = (uint32_t)(a->dx_seed & 0xffffffffu); p.dx_seed_hi = (uint32_t)(a->dx_seed >> 32);
+  p.dy_thr16 = a->dy_drop_p > 0.f ? drop_thr16(a->dy_drop_p) : 0;
+  p.dy_scale = 1.0f / (1.0f - a->dy_drop_p);
+  p.dy_seed_lo = (uint32_t)(a->dy_seed & 0xffffffffu); p.dy_seed_hi = (uint32_t)(a->dy_seed >> 32);
+  p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dbias = a->dbias;
+  p.rows = a->rows; p.d = (int)a->d;
+  const int key = (a->x_f32 ? 4 : 0) | (a->dy_f32 ? 2 : 0) | (a->dx_f32 ? 1 : 0);
+  switch (key) {
+    case 0: return launch_ln_bwd<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(p, stream);
+    case 5: return launch_ln_bwd<float, __nv_bfloat16, float>(p, stream);
+    case 6: return launch_ln_bwd<float, float, __nv_bfloat16>(p, stream);
+    case 4: return launch_ln_bwd<float, __nv_bfloat16, __nv_bfloat16>(p, stream);
+    default:
+      set_last_error("m3p_layernorm_bwd: unsupported dtype combination x_f32=%d dy_f32=%d dx_f32=%d", a->x_f32,
+                     a->dy_f32, a->dx_f32);
+      return M3P_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int m3p_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int64_t n, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(x && out, "m3p_colsum_bf16: null pointer");
+  M3P_REQUIRE(rows > 0 && n > 0 && n % 8 == 0 && ld % 8 == 0, "m3p_colsum_bf16: n and ld must be multiples of 8");
+  const int gy = (int)((n / 8 + EW_THREADS - 1) / EW_THREADS);
+  int gx = sm_count() * 4 / gy;
+  if (gx < 1) gx = 1;
+  if (gx > rows) gx = (int)rows;
+  const long long rpc = (rows + gx - 1) / gx;
+  gx = (int)((rows + rpc - 1) / rpc);
+  colsum_kernel<<<dim3(gx, gy), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, out, rows,
+                                                        (int)n, rpc);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_cast_f32_bf16(const float* in, void* out, int64_t n, float scale, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(in && out, "m3p_cast_f32_bf16: null pointer");
+  M3P_REQUIRE(n > 0 && n % 8 == 0, "m3p_cast_f32_bf16: n must be a positive multiple of 8");
+  const long long n8 = n / 8;
+  long long g = (n8 + EW_THREADS - 1) / EW_THREADS;
+  const long long cap = (long long)sm_count() * 16;
+  cast_f32_bf16_kernel<<<(int)(g < cap ? g : cap), EW_THREADS, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n8, scale);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_permute_cast_f32_bf16(const float* in, void* out, int64_t A, int64_t B, int64_t F,
+                                         m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(in && out, "m3p_permute_cast_f32_bf16: null pointer");
+  M3P_REQUIRE(A > 0 && B > 0 && F > 0 && F % 8 == 0, "m3p_permute_cast_f32_bf16: F must be a multiple of 8");
+  const long long total = A * B * (F / 8);
+  long long g = (total + EW_THREADS - 1) / EW_THREADS;
+  const long long cap = (long long)sm_count() * 16;
+  permute_cast_kernel<<<(int)(g < cap ? g : cap), EW_THREADS, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                         (int)A, (int)B, (int)(F / 8));
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_gather_rows_bf16(const void* src, const int64_t* flat_idx, int64_t n_inner, int64_t stride_outer,
+                                    int64_t stride_inner, void* dst, int64_t n, int64_t d, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(src && flat_idx && dst, "m3p_gather_rows_bf16: null pointer");
+  M3P_REQUIRE(n > 0 && d % 8 == 0 && stride_outer % 8 == 0 && stride_inner % 8 == 0 && n_inner > 0,
+              "m3p_gather_rows_bf16: d and strides must be multiples of 8");
+  gather_rows_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), flat_idx, n_inner,
+                                                            stride_outer, stride_inner,
+                                                            reinterpret_cast<__nv_bfloat16*>(dst), n, (int)d);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_scatter_rows_bf16(const void* src, const int64_t* flat_idx, int64_t n_inner, int64_t stride_outer,
+                                     int64_t stride_inner, void* dst, int64_t n, int64_t d, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(src && flat_idx && dst, "m3p_scatter_rows_bf16: null pointer");
+  M3P_REQUIRE(n > 0 && d % 8 == 0 && stride_outer % 8 == 0 && stride_inner % 8 == 0 && n_inner > 0,
+              "m3p_scatter_rows_bf16: d and strides must be multiples of 8");
+  scatter_rows_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), flat_idx, n_inner,
+                                                             stride_outer, stride_inner,
+                                                             reinterpret_cast<__nv_bfloat16*>(dst), n, (int)d);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_cross_entropy(const void* logits, int64_t ld, const int64_t* y, int64_t n, int64_t V,
+                                 int64_t ignore_index, float* loss, float* inv_count, void* dlogits, int64_t ldd,
+                                 m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(logits && y && loss && inv_count && dlogits, "m3p_cross_entropy: null pointer");
+  M3P_REQUIRE(n > 0 && V > 0 && ld % 8 == 0 && ldd % 8 == 0 && ld >= V && ldd >= V,
+              "m3p_cross_entropy: pitches must be multiples of 8 and >= V");
+  M3P_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+  ce_count_kernel<<<1, 256, 0, stream>>>(y, n, ignore_index, inv_count);
+  ce_row_kernel<<<(unsigned)n, EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, y, (int)V,
+                                                        ignore_index, inv_count, loss,
+                                                        reinterpret_cast<__nv_bfloat16*>(dlogits), ldd);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_rowdot_fwd(const void* x, const float* w, const float* bias, float* out, int64_t rows, int64_t d,
+                              m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(x && w && bias && out && rows > 0 && d > 0, "m3p_rowdot_fwd: bad arguments");
+  rowdot_fwd_kernel<<<(unsigned)((rows + EW_WARPS - 1) / EW_WARPS), EW_THREADS, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), w, bias, out, rows, (int)d);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_rowdot_bwd(const float* dout, const void* x, const float* w, void* dx, float* dw, float* db,
+                              int64_t rows, int64_t d, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(dout && x && w && dx && dw && db && rows > 0 && d > 0, "m3p_rowdot_bwd: bad arguments");
+  rowdot_bwd_kernel<<<(unsigned)((d + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, stream>>>(
+      dout, reinterpret_cast<const __nv_bfloat16*>(x), w, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, rows, (int)d);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_scatter_add_rows_f32(const float* src, const int64_t* idx, int64_t skip_index, float* dst, int64_t n,
+                                        int64_t d, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(src && idx && dst && n > 0 && d > 0 && d % 4 == 0, "m3p_scatter_add_rows_f32: bad arguments");
+  scatter_add_rows_f32_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(src, idx, skip_index, dst, n, (int)d);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
