@@ -106,6 +106,31 @@ M3P_API int m3p_gemm_bf16_debug(const m3p_gemm_args* args, int32_t a_lbo, int32_
 
 
 /* ------------------------------------------------------------------------------------------
+ * Fused self-attention (tcgen05): MultiHeadAttention.forward self-attn branch, transformer.py:149-210
+ * minus the four projections (those are m3p_gemm_bf16 calls):
+ *   scores = scale * q k^T ; scores[:, key >= seqlen[b]] = -inf (:199-200) ; w = softmax_fp32 (:202) ;
+ *   w = dropout(w, drop_p) (:203) ; ctx = w v (:204), heads re-interleaved as `unshape` (:176,205).
+ * qkv is the packed projection output [B*S][3*d] = [q | k | v], d = H*64 (head dim must be 64),
+ * head h in columns h*64..h*64+63 of each third.  S <= 256.  The score matrix never leaves the SM.
+ * lse [B][H][S] (fp32, log2 domain) is stashed for the backward, which recomputes the weights and
+ * returns dqkv in the same packed layout (dq already includes `scale`).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct m3p_attn_args {
+  const void* qkv;       /* bf16 [B*S][3*d] */
+  const int32_t* seqlen; /* [B] number of valid keys of each sequence */
+  int64_t B, S, H;
+  float scale; /* 1/sqrt(head dim), applied to the scores (== q / sqrt(dh), :197) */
+  float drop_p;
+  uint64_t seed;
+  void* ctx;  /* bf16 [B*S][d]: output of fwd, input of bwd */
+  float* lse; /* [B*H*S]: output of fwd, input of bwd */
+  const void* dctx; /* bwd: bf16 [B*S][d] */
+  void* dqkv;       /* bwd: bf16 [B*S][3*d] */
+} m3p_attn_args;
+M3P_API int m3p_attention_fwd(const m3p_attn_args* args, m3p_stream_t stream);
+M3P_API int m3p_attention_bwd(const m3p_attn_args* args, m3p_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * LayerNorm (eps 1e-12, biased variance, affine) over the last dim of a bf16 [rows][d] tensor.
  * Replaces layer_norm1 / layer_norm2 + the `tensor *= mask` that follows layer_norm2
  * (transformer.py:953,957-958) and BertPredictionHeadTransform.LayerNorm (:605).
@@ -150,6 +175,9 @@ M3P_API int m3p_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows,
 
 /* out = bf16(scale * in): refreshes the bf16 tensor-core copies of the fp32 master parameters. */
 M3P_API int m3p_cast_f32_bf16(const float* in, void* out, int64_t n, float scale, m3p_stream_t stream);
+/* du = dg * gelu_erf'(u), bf16: backward of the activation of BertPredictionHeadTransform
+ * (transformer.py:603-604; the FFN's GELU backward is fused into a GEMM epilogue instead). */
+M3P_API int m3p_gelu_bwd(const void* dg, const void* u, void* du, int64_t n, m3p_stream_t stream);
 /* (A,B,F) fp32 -> (B,A,F) bf16: the reference's sequence-first inputs (x_img (R,bs,2048),
  * transformer.py:895) to batch-major GEMM rows. */
 M3P_API int m3p_permute_cast_f32_bf16(const float* in, void* out, int64_t A, int64_t B, int64_t F,
@@ -163,18 +191,25 @@ M3P_API int m3p_gather_rows_bf16(const void* src, const int64_t* flat_idx, int64
 M3P_API int m3p_scatter_rows_bf16(const void* src, const int64_t* flat_idx, int64_t n_inner, int64_t stride_outer,
                                   int64_t stride_inner, void* dst, int64_t n, int64_t d, m3p_stream_t stream);
 
-/* F.cross_entropy(logits, y, reduction='mean', ignore_index) forward AND backward in one pass pair
- * (transformer.py:112 MLM, :581 MRM): *loss = mean over non-ignored rows; dlogits = dloss/dlogits
- * (bf16, same shape, pitch ldd); inv_count (device scalar) receives 1/#valid rows. */
-M3P_API int m3p_cross_entropy(const void* logits, int64_t ld, const int64_t* y, int64_t n, int64_t V,
-                              int64_t ignore_index, float* loss, float* inv_count, void* dlogits, int64_t ldd,
-                              m3p_stream_t stream);
+/* F.cross_entropy(logits, y, reduction='mean', ignore_index) over bf16 logits (transformer.py:112 MLM,
+ * :581 MRM).  Forward: *loss = mean over non-ignored rows, lse[n] (natural log) and *inv_count =
+ * 1/#valid rows are stashed.  Backward: dlogits = g * (softmax - onehot) * inv_count (0 on ignored
+ * rows), g = *grad_scale (device scalar: the upstream dloss, read on the device so the host never
+ * syncs) or 1 when NULL; dlogits may alias logits (same pitch). */
+M3P_API int m3p_cross_entropy_fwd(const void* logits, int64_t ld, const int64_t* y, int64_t n, int64_t V,
+                                  int64_t ignore_index, float* loss, float* lse, float* inv_count,
+                                  m3p_stream_t stream);
+M3P_API int m3p_cross_entropy_bwd(const void* logits, int64_t ld, const int64_t* y, int64_t n, int64_t V,
+                                  int64_t ignore_index, const float* lse, const float* inv_count,
+                                  const float* grad_scale, void* dlogits, int64_t ldd, m3p_stream_t stream);
 
-/* seq_relationship / seq_relationship2: Linear(d, 1) (transformer.py:713,716,1196,1200) and backward. */
+/* seq_relationship / seq_relationship2: Linear(d, 1) (transformer.py:713,716,1196,1200) and backward.
+ * tanh_grad != 0: x is the BertPooler tanh output (:556-557) and dx is returned w.r.t. the
+ * pre-activation, dx = dout * w * (1 - x^2). */
 M3P_API int m3p_rowdot_fwd(const void* x, const float* w, const float* bias, float* out, int64_t rows, int64_t d,
                            m3p_stream_t stream);
 M3P_API int m3p_rowdot_bwd(const float* dout, const void* x, const float* w, void* dx, float* dw, float* db,
-                           int64_t rows, int64_t d, m3p_stream_t stream);
+                           int64_t rows, int64_t d, int32_t tanh_grad, m3p_stream_t stream);
 
 /* dst[idx[i]][:] += src[i][:] (fp32, atomic), rows with idx == skip_index skipped. */
 M3P_API int m3p_scatter_add_rows_f32(const float* src, const int64_t* idx, int64_t skip_index, float* dst, int64_t n,

@@ -1,0 +1,540 @@
+// Fused self-attention of MultiHeadAttention.forward (reference transformer.py:149-210, self-attn
+// branch) and its backward, on tcgen05 tensor cores.
+//
+//   scores = (q / sqrt(dh)) k^T ; key-padding mask -> -inf ; softmax in fp32 ; dropout ; ctx = w v
+//
+// The whole joint sequence (S = 100 regions + 128 tokens = 228 <= 256 keys) fits one CTA, so there
+// is no online-softmax rescaling: S = Q K^T lands in TMEM in one shot (128 query rows x <=256 key
+// columns of fp32), each thread owns one query row for max / exp2 / sum, P is written as bf16 into
+// 128B-swizzled shared memory (exactly the layout TMA would have produced) and fed back to the
+// tensor core as the A operand of O = P V.  The score matrix never touches HBM (the reference
+// materialises it >= 4 times per layer).
+//
+// Operands come straight out of the packed QKV projection [B*S][3d] through 3-D TMA maps
+// (dim0 = feature, dim1 = position in sequence, dim2 = sequence), so rows beyond S are zero-filled
+// by the TMA unit and no padding copies exist.  Head dim is 64 (= one 128-byte swizzle row), which
+// holds for M3P-base (768/12) and M3P-large (1024/16).
+//
+// Forward : grid = B*H*ceil(S/128) CTAs of 128 threads, 96 KB smem, 256 TMEM columns -> 2 CTAs/SM,
+//           so one CTA's softmax overlaps the other's MMAs.
+// Backward: grid = B*H CTAs of 256 threads; 128x128 (query x key) blocks; S and dP recomputed into
+//           TMEM, dQ/dK/dV accumulate in TMEM (512 columns used), P and dS staged through smem
+//           and consumed both K-major (dQ) and MN-major (dK, dV) without a transpose.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace m3p {
+
+constexpr int ATT_DH = 64;
+constexpr int ATT_MAX_S = 256;
+constexpr uint32_t TILE16K = 128 * 128;  // [128 rows][128 B]
+
+struct AttnKernelParams {
+  int B, S, H, d;
+  int n_kv;  // S rounded up to 16: N of the score MMA and K of the PV MMA
+  int MT;    // ceil(S / 128)
+  float scale, scale_log2;
+  const int32_t* seqlen;
+  __nv_bfloat16* ctx;
+  float* lse;  // [B][H][S], log2 domain: max*scale*log2e + log2(sum)
+  const __nv_bfloat16* ctx_in;   // backward: forward output (for delta)
+  const __nv_bfloat16* dctx;     // backward
+  __nv_bfloat16* dqkv;           // backward
+  uint32_t thr16, seed_lo, seed_hi;
+  float drop_scale;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// byte offset of the 16-byte chunk c16 (0..7) of row `row` inside a [rows][128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t swz_off(int row, int c16) {
+  return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(c16 ^ (row & 7)) << 4);
+}
+
+// dropout keep-scales for 32 consecutive keys starting at key0 (multiple of 32) of query row q
+__device__ __forceinline__ uint32_t attn_drop_base(int bh, int q, int key0) {
+  return (static_cast<uint32_t>(bh) * ATT_MAX_S + static_cast<uint32_t>(q)) * ATT_MAX_S +
+         static_cast<uint32_t>(key0);
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+constexpr uint32_t FWD_SMEM_TILES = 96 * 1024;  // sQ 16K | sK 32K | pad 16K | sV 32K ; sP aliases first 64K
+constexpr uint32_t FWD_SMEM_BYTES = FWD_SMEM_TILES + 64 + 1024;
+
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                const AttnKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16 * 1024;
+  uint8_t* sV = smem + 64 * 1024;
+  uint8_t* sP = smem;  // written only after the score MMA has consumed sQ / sK
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + FWD_SMEM_TILES);
+  uint64_t* bar_v = bar_qk + 1;
+  uint64_t* bar_s = bar_qk + 2;
+  uint64_t* bar_o = bar_qk + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int u = blockIdx.x;
+  const int mt = u % p.MT;
+  const int h = (u / p.MT) % p.H;
+  const int b = u / (p.MT * p.H);
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_kv);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_qk, 48 * 1024);
+    tma_load_3d(sQ, &tmap_q, bar_qk, h * ATT_DH, mt * 128, b);
+    tma_load_3d(sK, &tmap_kv, bar_qk, p.d + h * ATT_DH, 0, b);
+    mbar_arrive_expect_tx(bar_v, 32 * 1024);
+    tma_load_3d(sV, &tmap_kv, bar_v, 2 * p.d + h * ATT_DH, 0, b);
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, p.n_kv, 0, 0);
+    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+#pragma unroll
+    for (int k = 0; k < ATT_DH / 16; ++k)
+      umma_ss(tmem_base, make_smem_desc(qa + k * 32, 0, 1024), make_smem_desc(ka + k * 32, 0, 1024), idesc,
+              k > 0 ? 1u : 0u);
+    umma_commit(bar_s);
+  }
+  __syncwarp();
+  mbar_wait(bar_s, 0);
+  __syncwarp();
+  tc_fence_after();
+
+  // ---- softmax: one thread per query row ----
+  const int row = warp * 32 + lane;
+  const int q_idx = mt * 128 + row;
+  int L = p.seqlen[b];
+  L = L < 0 ? 0 : (L > p.S ? p.S : L);
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const int nchunk = (p.n_kv + 31) >> 5;
+  float mx = -INFINITY;
+  for (int c = 0; c < nchunk; ++c) {
+    uint32_t acc[32];
+    tmem_ld_32x32b_x32(t_row + c * 32, acc);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c * 32 + j < L) mx = fmaxf(mx, __uint_as_float(acc[j]));
+  }
+  const float mxs = (L > 0) ? mx * p.scale_log2 : 0.f;
+  float sum = 0.f;
+  const int bh = b * p.H + h;
+  for (int c = 0; c < nchunk; ++c) {
+    uint32_t acc[32];
+    tmem_ld_32x32b_x32(t_row + c * 32, acc);
+    tmem_ld_wait();
+    float pv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float e = ex2(fmaf(__uint_as_float(acc[j]), p.scale_log2, -mxs));
+      pv[j] = (c * 32 + j < L) ? e : 0.f;
+      sum += pv[j];
+    }
+    if (p.thr16 != 0) {
+      const uint32_t e0 = attn_drop_base(bh, q_idx, c * 32);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t hsh = drop_hash((e0 >> 1) + j, p.seed_lo, p.seed_hi);
+        pv[2 * j] = ((hsh & 0xffffu) >= p.thr16) ? pv[2 * j] * p.drop_scale : 0.f;
+        pv[2 * j + 1] = ((hsh >> 16) >= p.thr16) ? pv[2 * j + 1] * p.drop_scale : 0.f;
+      }
+    }
+    // keys [c*32, c*32+32) live in k-block c/2, 16-byte chunks (c&1)*4 .. +3 of this row
+    uint8_t* blk = sP + (c >> 1) * TILE16K;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 v = make_uint4(pack_bf16x2(pv[8 * g + 0], pv[8 * g + 1]), pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]),
+                                 pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]), pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]));
+      *reinterpret_cast<uint4*>(blk + swz_off(row, (c & 1) * 4 + g)) = v;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    mbar_wait(bar_v, 0);
+    const uint32_t idesc = make_idesc_bf16(128, ATT_DH, 0, 1);
+    const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+    const int nk = p.n_kv >> 4;
+    for (int kk = 0; kk < nk; ++kk) {
+      const uint64_t adesc = make_smem_desc(pa + (kk >> 2) * TILE16K + (kk & 3) * 32, 0, 1024);
+      const uint64_t bdesc = make_smem_desc(va + kk * 2048, 256 * 128, 1024);
+      umma_ss(tmem_base, adesc, bdesc, idesc, kk > 0 ? 1u : 0u);
+    }
+    umma_commit(bar_o);
+  }
+  __syncwarp();
+  mbar_wait(bar_o, 0);
+  __syncwarp();
+  tc_fence_after();
+
+  {
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+    uint32_t o0[32], o1[32];
+    tmem_ld_32x32b_x32(t_row, o0);
+    tmem_ld_32x32b_x32(t_row + 32, o1);
+    tmem_ld_wait();
+    if (q_idx < p.S) {
+      __nv_bfloat16* op = p.ctx + (static_cast<long long>(b) * p.S + q_idx) * p.d + h * ATT_DH;
+      uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        o4[g] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * g + 0]) * inv, __uint_as_float(o0[8 * g + 1]) * inv),
+                           pack_bf16x2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
+                           pack_bf16x2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
+                           pack_bf16x2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv));
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        o4[4 + g] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * g + 0]) * inv, __uint_as_float(o1[8 * g + 1]) * inv),
+                               pack_bf16x2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv),
+                               pack_bf16x2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv),
+                               pack_bf16x2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv));
+      p.lse[(static_cast<long long>(bh)) * p.S + q_idx] = (sum > 0.f) ? mxs + log2f(sum) : INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+// smem: sQ | sK | sV | sdO (each [256 rows][128 B]) | sP | sdS (each 2 k-blocks of [128 rows][128 B])
+constexpr uint32_t BWD_SMEM_TILES = 6 * 32 * 1024;
+constexpr uint32_t BWD_SMEM_BYTES = BWD_SMEM_TILES + 2 * ATT_MAX_S * 4 + 64 + 1024;
+constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 384, TM_DV = 448;
+
+__device__ __forceinline__ void store_acc32(__nv_bfloat16* dst, const uint32_t* acc, float mul) {
+  uint4* o4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    o4[g] = make_uint4(pack_bf16x2(__uint_as_float(acc[8 * g + 0]) * mul, __uint_as_float(acc[8 * g + 1]) * mul),
+                       pack_bf16x2(__uint_as_float(acc[8 * g + 2]) * mul, __uint_as_float(acc[8 * g + 3]) * mul),
+                       pack_bf16x2(__uint_as_float(acc[8 * g + 4]) * mul, __uint_as_float(acc[8 * g + 5]) * mul),
+                       pack_bf16x2(__uint_as_float(acc[8 * g + 6]) * mul, __uint_as_float(acc[8 * g + 7]) * mul));
+}
+
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                const AttnKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 32 * 1024;
+  uint8_t* sV = smem + 64 * 1024;
+  uint8_t* sdO = smem + 96 * 1024;
+  uint8_t* sP = smem + 128 * 1024;
+  uint8_t* sdS = smem + 160 * 1024;
+  float* s_delta = reinterpret_cast<float*>(smem + BWD_SMEM_TILES);
+  float* s_lse = s_delta + ATT_MAX_S;
+  uint64_t* bar_ld = reinterpret_cast<uint64_t*>(s_lse + ATT_MAX_S);
+  uint64_t* bar_sd = bar_ld + 1;
+  uint64_t* bar_g = bar_ld + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ld + 3);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.x % p.H;
+  const int b = blockIdx.x / p.H;
+  const int bh = blockIdx.x;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmap_qkv);
+    prefetch_tmap(&tmap_do);
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_sd, 1);
+    mbar_init(bar_g, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_ld, 4 * 32 * 1024);
+    tma_load_3d(sQ, &tmap_qkv, bar_ld, h * ATT_DH, 0, b);
+    tma_load_3d(sK, &tmap_qkv, bar_ld, p.d + h * ATT_DH, 0, b);
+    tma_load_3d(sV, &tmap_qkv, bar_ld, 2 * p.d + h * ATT_DH, 0, b);
+    tma_load_3d(sdO, &tmap_do, bar_ld, h * ATT_DH, 0, b);
+  }
+
+  // ---- delta = rowsum(dO * O), lse: one thread per query row (global reads overlap the TMA) ----
+  {
+    const int r = threadIdx.x;
+    float dl = 0.f, ls = 0.f;
+    if (r < p.S) {
+      const long long off = (static_cast<long long>(b) * p.S + r) * p.d + h * ATT_DH;
+      const uint4* a4 = reinterpret_cast<const uint4*>(p.dctx + off);
+      const uint4* o4 = reinterpret_cast<const uint4*>(p.ctx_in + off);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 a = __ldg(a4 + g), o = __ldg(o4 + g);
+        dl = fmaf(bf16_lo(a.x), bf16_lo(o.x), dl); dl = fmaf(bf16_hi(a.x), bf16_hi(o.x), dl);
+        dl = fmaf(bf16_lo(a.y), bf16_lo(o.y), dl); dl = fmaf(bf16_hi(a.y), bf16_hi(o.y), dl);
+        dl = fmaf(bf16_lo(a.z), bf16_lo(o.z), dl); dl = fmaf(bf16_hi(a.z), bf16_hi(o.z), dl);
+        dl = fmaf(bf16_lo(a.w), bf16_lo(o.w), dl); dl = fmaf(bf16_hi(a.w), bf16_hi(o.w), dl);
+      }
+      ls = p.lse[static_cast<long long>(bh) * p.S + r];
+    }
+    s_delta[r] = dl;
+    s_lse[r] = ls;
+  }
+  __syncthreads();
+
+  int L = p.seqlen[b];
+  L = L < 0 ? 0 : (L > p.S ? p.S : L);
+  const int NT = p.MT;
+  const int w4 = warp & 3, half = warp >> 2;
+  const int row = w4 * 32 + lane;
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
+  const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // S, dP : K-major A and B
+  const uint32_t idesc_t = make_idesc_bf16(128, ATT_DH, 1, 1);  // dV, dK: MN-major A and B
+  const uint32_t idesc_q = make_idesc_bf16(128, ATT_DH, 0, 1);  // dQ    : K-major A, MN-major B
+  uint32_t ph_sd = 0, ph_g = 0;
+  int g_pending = 0;
+
+  for (int j = 0; j < NT; ++j) {
+    for (int i = 0; i < NT; ++i) {
+      if (threadIdx.x == 0) {
+        if (i == 0 && j == 0) mbar_wait(bar_ld, 0);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(sQ) + i * TILE16K, ka = smem_u32(sK) + j * TILE16K;
+        const uint32_t da = smem_u32(sdO) + i * TILE16K, va = smem_u32(sV) + j * TILE16K;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem_base + TM_S, make_smem_desc(qa + k * 32, 0, 1024), make_smem_desc(ka + k * 32, 0, 1024),
+                  idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem_base + TM_DP, make_smem_desc(da + k * 32, 0, 1024), make_smem_desc(va + k * 32, 0, 1024),
+                  idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_sd);
+      }
+      __syncwarp();
+      mbar_wait(bar_sd, ph_sd);
+      ph_sd ^= 1;
+      // the previous block's dV/dK/dQ MMAs still read sP / sdS: wait before overwriting them
+      if (g_pending) {
+        mbar_wait(bar_g, ph_g);
+        ph_g ^= 1;
+        g_pending = 0;
+      }
+      __syncwarp();
+      tc_fence_after();
+
+      const int q = i * 128 + row;
+      const bool q_ok = q < p.S;
+      const float lse2 = s_lse[q], delta = s_delta[q];
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = half * 64 + c * 32;  // column inside the 128-key tile
+        uint32_t sacc[32], dacc[32];
+        tmem_ld_32x32b_x32(t_lane + TM_S + col0, sacc);
+        tmem_ld_32x32b_x32(t_lane + TM_DP + col0, dacc);
+        tmem_ld_wait();
+        const int key0 = j * 128 + col0;
+        float pd[32], ds[32];
+        uint32_t e0 = 0;
+        if (p.thr16 != 0) e0 = attn_drop_base(bh, q, key0);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const bool ok = q_ok && (key0 + jj < L);
+          const float pr = ok ? ex2(fmaf(__uint_as_float(sacc[jj]), p.scale_log2, -lse2)) : 0.f;
+          float ks = 1.0f;
+          if (p.thr16 != 0) {
+            const uint32_t hsh = drop_hash((e0 >> 1) + (jj >> 1), p.seed_lo, p.seed_hi);
+            const uint32_t hv = (jj & 1) ? (hsh >> 16) : (hsh & 0xffffu);
+            ks = (hv >= p.thr16) ? p.drop_scale : 0.f;
+          }
+          pd[jj] = pr * ks;
+          ds[jj] = ok ? pr * (__uint_as_float(dacc[jj]) * ks - delta) * p.scale : 0.f;
+        }
+        uint8_t* pblk = sP + half * TILE16K;
+        uint8_t* dblk = sdS + half * TILE16K;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t off = swz_off(row, c * 4 + g);
+          *reinterpret_cast<uint4*>(pblk + off) =
+              make_uint4(pack_bf16x2(pd[8 * g + 0], pd[8 * g + 1]), pack_bf16x2(pd[8 * g + 2], pd[8 * g + 3]),
+                         pack_bf16x2(pd[8 * g + 4], pd[8 * g + 5]), pack_bf16x2(pd[8 * g + 6], pd[8 * g + 7]));
+          *reinterpret_cast<uint4*>(dblk + off) =
+              make_uint4(pack_bf16x2(ds[8 * g + 0], ds[8 * g + 1]), pack_bf16x2(ds[8 * g + 2], ds[8 * g + 3]),
+                         pack_bf16x2(ds[8 * g + 4], ds[8 * g + 5]), pack_bf16x2(ds[8 * g + 6], ds[8 * g + 7]));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS);
+        const uint32_t doa = smem_u32(sdO) + i * TILE16K, qa = smem_u32(sQ) + i * TILE16K;
+        const uint32_t ka = smem_u32(sK) + j * TILE16K;
+        // dV_j += Pd^T dO_i ; dK_j += dS^T Q_i      (M = 128 keys, N = 64, K = 128 queries)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tmem_base + TM_DV, make_smem_desc(pa + k * 2048, TILE16K, 1024),
+                  make_smem_desc(doa + k * 2048, TILE16K, 1024), idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tmem_base + TM_DK, make_smem_desc(sa + k * 2048, TILE16K, 1024),
+                  make_smem_desc(qa + k * 2048, TILE16K, 1024), idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+        // dQ_i += dS K_j                             (M = 128 queries, N = 64, K = 128 keys)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tmem_base + TM_DQ + i * ATT_DH, make_smem_desc(sa + (k >> 2) * TILE16K + (k & 3) * 32, 0, 1024),
+                  make_smem_desc(ka + k * 2048, TILE16K, 1024), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_g);
+      }
+      g_pending = 1;
+    }
+    // ---- dK_j, dV_j complete: TMEM -> bf16 -> dqkv ----
+    __syncwarp();
+    mbar_wait(bar_g, ph_g);
+    ph_g ^= 1;
+    g_pending = 0;
+    __syncwarp();
+    tc_fence_after();
+    {
+      uint32_t a[32], v[32];
+      tmem_ld_32x32b_x32(t_lane + TM_DK + half * 32, a);
+      tmem_ld_32x32b_x32(t_lane + TM_DV + half * 32, v);
+      tmem_ld_wait();
+      const int key = j * 128 + row;
+      if (key < p.S) {
+        __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.S + key) * (3 * p.d) + h * ATT_DH + half * 32;
+        store_acc32(base + p.d, a, 1.0f);
+        store_acc32(base + 2 * p.d, v, 1.0f);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  // ---- dQ ----
+  tc_fence_after();
+  for (int i = 0; i < NT; ++i) {
+    uint32_t a[32];
+    tmem_ld_32x32b_x32(t_lane + TM_DQ + i * ATT_DH + half * 32, a);
+    tmem_ld_wait();
+    const int q = i * 128 + row;
+    if (q < p.S) {
+      __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.S + q) * (3 * p.d) + h * ATT_DH + half * 32;
+      store_acc32(base, a, 1.0f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int fill_params(const m3p_attn_args* a, AttnKernelParams& p, const char* who) {
+  M3P_REQUIRE(a != nullptr, "%s: null args", who);
+  M3P_REQUIRE(a->qkv && a->seqlen && a->ctx && a->lse, "%s: null pointer", who);
+  M3P_REQUIRE(a->B > 0 && a->H > 0 && a->S > 0, "%s: empty problem", who);
+  M3P_REQUIRE(a->S <= ATT_MAX_S, "%s: sequence length %lld > %d is not supported by the single-tile kernel", who,
+              (long long)a->S, ATT_MAX_S);
+  M3P_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, "%s: drop_p out of range", who);
+  M3P_REQUIRE(a->B * a->H < (1ll << 22), "%s: too many (sequence, head) pairs", who);
+  p.B = (int)a->B; p.S = (int)a->S; p.H = (int)a->H; p.d = (int)a->H * ATT_DH;
+  p.n_kv = (p.S + 15) & ~15;
+  p.MT = (p.S + 127) / 128;
+  p.scale = a->scale;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.seqlen = a->seqlen;
+  p.ctx = reinterpret_cast<__nv_bfloat16*>(a->ctx);
+  p.ctx_in = reinterpret_cast<const __nv_bfloat16*>(a->ctx);
+  p.lse = a->lse;
+  p.dctx = reinterpret_cast<const __nv_bfloat16*>(a->dctx);
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv);
+  p.thr16 = a->drop_p > 0.f ? drop_thr16(a->drop_p) : 0;
+  p.drop_scale = 1.0f / (1.0f - a->drop_p);
+  p.seed_lo = (uint32_t)(a->seed & 0xffffffffu);
+  p.seed_hi = (uint32_t)(a->seed >> 32);
+  return M3P_OK;
+}
+
+}  // namespace m3p
+
+using namespace m3p;
+
+extern "C" int m3p_attention_fwd(const m3p_attn_args* a, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  AttnKernelParams p{};
+  int rc = fill_params(a, p, "m3p_attention_fwd");
+  if (rc) return rc;
+  CUtensorMap tq, tkv;
+  const uint64_t d3 = 3ull * p.d;
+  rc = get_tmap_3d_bf16(&tq, a->qkv, d3, (uint64_t)p.S, (uint64_t)p.B, d3, d3 * p.S, ATT_DH, 128, 1);
+  if (rc) return rc;
+  rc = get_tmap_3d_bf16(&tkv, a->qkv, d3, (uint64_t)p.S, (uint64_t)p.B, d3, d3 * p.S, ATT_DH, 256, 1);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    M3P_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_BYTES));
+    attr_set = true;
+  }
+  attn_fwd_kernel<<<p.B * p.H * p.MT, 128, FWD_SMEM_BYTES, stream>>>(tq, tkv, p);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_attention_bwd(const m3p_attn_args* a, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  AttnKernelParams p{};
+  int rc = fill_params(a, p, "m3p_attention_bwd");
+  if (rc) return rc;
+  M3P_REQUIRE(a->dctx && a->dqkv, "m3p_attention_bwd: dctx / dqkv missing");
+  CUtensorMap tqkv, tdo;
+  const uint64_t d3 = 3ull * p.d, d1 = (uint64_t)p.d;
+  rc = get_tmap_3d_bf16(&tqkv, a->qkv, d3, (uint64_t)p.S, (uint64_t)p.B, d3, d3 * p.S, ATT_DH, 256, 1);
+  if (rc) return rc;
+  rc = get_tmap_3d_bf16(&tdo, a->dctx, d1, (uint64_t)p.S, (uint64_t)p.B, d1, d1 * p.S, ATT_DH, 256, 1);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    M3P_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
+    attr_set = true;
+  }
+  attn_bwd_kernel<<<p.B * p.H, 256, BWD_SMEM_BYTES, stream>>>(tqkv, tdo, p);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}

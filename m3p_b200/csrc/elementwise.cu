@@ -278,6 +278,22 @@ permute_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ ou
   }
 }
 
+// du = dg * gelu_erf'(u): backward of the GELU inside BertPredictionHeadTransform (transformer.py:603-604),
+// where the LayerNorm backward sits between the next linear's dgrad and this activation.
+__global__ void __launch_bounds__(EW_THREADS)
+gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dg, const __nv_bfloat16* __restrict__ u,
+                __nv_bfloat16* __restrict__ du, long long n8) {
+  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * EW_THREADS) {
+    float a[8], b[8];
+    load8(dg + i * 8, a);
+    load8(u + i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= gelu_erf_grad(b[j]);
+    store8(du + i * 8, a);
+  }
+}
+
 // =================================================================================================
 // row gather / scatter (prediction heads, FreeLB input grads)
 //   gather : dst[i][:] = src[rows[i]][:]            (src addressed as base + row_t*stride_t + row_b*stride_b)
@@ -328,22 +344,26 @@ __global__ void ce_count_kernel(const int64_t* __restrict__ y, long long n, long
   if (threadIdx.x == 0) *inv_count = s_cnt > 0 ? 1.0f / (float)s_cnt : 0.f;  // 0 valid rows: torch gives nan; we give 0 grads
 }
 
+// (m, s) <- combine((m, s), (m2, s2)) for the online log-sum-exp
+__device__ __forceinline__ void lse_combine(float& m, float& s, float m2, float s2) {
+  const float mn = fmaxf(m, m2);
+  s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+  m = mn;
+}
+
 __global__ void __launch_bounds__(EW_THREADS)
-ce_row_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const int64_t* __restrict__ y, int V,
+ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const int64_t* __restrict__ y, int V,
               long long ignore_index, const float* __restrict__ inv_count, float* __restrict__ loss,
-              __nv_bfloat16* __restrict__ dlogits, long long ldd) {
+              float* __restrict__ lse_out) {
   __shared__ float s_m[EW_WARPS], s_s[EW_WARPS];
   const long long row = blockIdx.x;
   const __nv_bfloat16* lp = logits + row * ld;
-  __nv_bfloat16* dp = dlogits + row * ldd;
   const long long target = y[row];
-  const int nvec = V >> 3;
   if (target == ignore_index) {
-    for (int i = threadIdx.x; i < nvec; i += EW_THREADS) *reinterpret_cast<uint4*>(dp + i * 8) = make_uint4(0, 0, 0, 0);
-    for (int i = nvec * 8 + threadIdx.x; i < V; i += EW_THREADS) dp[i] = __float2bfloat16_rn(0.f);
+    if (threadIdx.x == 0) lse_out[row] = 0.f;
     return;
   }
-  // pass 1: online max / sum(exp)
+  const int nvec = V >> 3;
   float m = -INFINITY, s = 0.f;
   for (int i = threadIdx.x; i < nvec; i += EW_THREADS) {
     float v[8];
@@ -360,45 +380,55 @@ ce_row_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const int6
     if (v > m) { s *= __expf(m - v); m = v; }
     s += __expf(v - m);
   }
-  // warp then block combine of (m, s)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
     const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
-    const float mn = fmaxf(m, m2);
-    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
-    m = mn;
+    lse_combine(m, s, m2, s2);
   }
   if ((threadIdx.x & 31) == 0) { s_m[threadIdx.x >> 5] = m; s_s[threadIdx.x >> 5] = s; }
   __syncthreads();
-  m = s_m[0]; s = s_s[0];
+  if (threadIdx.x == 0) {
+    m = s_m[0]; s = s_s[0];
 #pragma unroll
-  for (int w = 1; w < EW_WARPS; ++w) {
-    const float m2 = s_m[w], s2 = s_s[w];
-    const float mn = fmaxf(m, m2);
-    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
-    m = mn;
+    for (int w = 1; w < EW_WARPS; ++w) lse_combine(m, s, s_m[w], s_s[w]);
+    const float lse = m + logf(s);
+    lse_out[row] = lse;
+    atomicAdd(loss, (lse - __bfloat162float(lp[target])) * (*inv_count));
   }
-  const float lse = m + __logf(s);
-  const float inv_n = *inv_count;
-  if (threadIdx.x == 0) atomicAdd(loss, (lse - __bfloat162float(lp[target])) * inv_n);
-  // pass 2: gradient
-  const float inv_s = 1.0f / s;
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const int64_t* __restrict__ y, int V,
+              long long ignore_index, const float* __restrict__ lse_in, const float* __restrict__ inv_count,
+              const float* __restrict__ grad_scale, __nv_bfloat16* __restrict__ dlogits, long long ldd) {
+  const long long row = blockIdx.x;
+  const __nv_bfloat16* lp = logits + row * ld;
+  __nv_bfloat16* dp = dlogits + row * ldd;
+  const long long target = y[row];
+  const int nvec = V >> 3;
+  if (target == ignore_index) {
+    for (int i = threadIdx.x; i < nvec; i += EW_THREADS) *reinterpret_cast<uint4*>(dp + i * 8) = make_uint4(0, 0, 0, 0);
+    for (int i = nvec * 8 + threadIdx.x; i < V; i += EW_THREADS) dp[i] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const float lse = lse_in[row];
+  const float g = (*inv_count) * (grad_scale != nullptr ? *grad_scale : 1.0f);
   for (int i = threadIdx.x; i < nvec; i += EW_THREADS) {
     float v[8];
     load8(lp + i * 8, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float pj = __expf(v[j] - m) * inv_s;
+      float pj = __expf(v[j] - lse);
       if (i * 8 + j == target) pj -= 1.0f;
-      v[j] = pj * inv_n;
+      v[j] = pj * g;
     }
     store8(dp + i * 8, v);
   }
   for (int i = nvec * 8 + threadIdx.x; i < V; i += EW_THREADS) {
-    float pj = __expf(__bfloat162float(lp[i]) - m) * inv_s;
+    float pj = __expf(__bfloat162float(lp[i]) - lse);
     if (i == target) pj -= 1.0f;
-    dp[i] = __float2bfloat16_rn(pj * inv_n);
+    dp[i] = __float2bfloat16_rn(pj * g);
   }
 }
 
@@ -416,19 +446,22 @@ rowdot_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
   acc = warp_sum(acc);
   if (lane == 0) out[row] = acc + bias[0];
 }
-// dx[row][j] = dout[row] * w[j] ; dw[j] += sum_rows dout[row] * x[row][j] ; db += sum dout
+// dx[row][j] = dout[row] * w[j] (* (1 - x^2) when x is a tanh output whose pre-activation gradient is
+// wanted: BertPooler, transformer.py:556-557) ; dw[j] += sum_rows dout[row] * x[row][j] ; db += sum dout
 __global__ void __launch_bounds__(EW_THREADS)
 rowdot_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
-                  __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long long rows, int d) {
+                  __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long long rows, int d,
+                  int tanh_grad) {
   const int j = blockIdx.x * EW_THREADS + threadIdx.x;
   if (j >= d) return;
   float acc = 0.f, accb = 0.f;
   const float wj = w[j];
   for (long long r = 0; r < rows; ++r) {
     const float g = dout[r];
-    acc += g * __bfloat162float(x[r * d + j]);
+    const float xv = __bfloat162float(x[r * d + j]);
+    acc += g * xv;
     accb += g;
-    dx[r * d + j] = __float2bfloat16_rn(g * wj);
+    dx[r * d + j] = __float2bfloat16_rn(tanh_grad ? g * wj * (1.0f - xv * xv) : g * wj);
   }
   atomicAdd(dw + j, acc);
   if (j == 0) atomicAdd(db, accb);
@@ -538,6 +571,20 @@ extern "C" int m3p_cast_f32_bf16(const float* in, void* out, int64_t n, float sc
   return M3P_OK;
 }
 
+extern "C" int m3p_gelu_bwd(const void* dg, const void* u, void* du, int64_t n, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(dg && u && du, "m3p_gelu_bwd: null pointer");
+  M3P_REQUIRE(n > 0 && n % 8 == 0, "m3p_gelu_bwd: n must be a positive multiple of 8");
+  const long long n8 = n / 8;
+  long long g = (n8 + EW_THREADS - 1) / EW_THREADS;
+  const long long cap = (long long)sm_count() * 16;
+  gelu_bwd_kernel<<<(int)(g < cap ? g : cap), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dg),
+                                                                     reinterpret_cast<const __nv_bfloat16*>(u),
+                                                                     reinterpret_cast<__nv_bfloat16*>(du), n8);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
 extern "C" int m3p_permute_cast_f32_bf16(const float* in, void* out, int64_t A, int64_t B, int64_t F,
                                          m3p_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -578,17 +625,29 @@ extern "C" int m3p_scatter_rows_bf16(const void* src, const int64_t* flat_idx, i
   return M3P_OK;
 }
 
-extern "C" int m3p_cross_entropy(const void* logits, int64_t ld, const int64_t* y, int64_t n, int64_t V,
-                                 int64_t ignore_index, float* loss, float* inv_count, void* dlogits, int64_t ldd,
-                                 m3p_stream_t stream_) {
+extern "C" int m3p_cross_entropy_fwd(const void* logits, int64_t ld, const int64_t* y, int64_t n, int64_t V,
+                                     int64_t ignore_index, float* loss, float* lse, float* inv_count,
+                                     m3p_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  M3P_REQUIRE(logits && y && loss && inv_count && dlogits, "m3p_cross_entropy: null pointer");
-  M3P_REQUIRE(n > 0 && V > 0 && ld % 8 == 0 && ldd % 8 == 0 && ld >= V && ldd >= V,
-              "m3p_cross_entropy: pitches must be multiples of 8 and >= V");
+  M3P_REQUIRE(logits && y && loss && lse && inv_count, "m3p_cross_entropy_fwd: null pointer");
+  M3P_REQUIRE(n > 0 && V > 0 && ld % 8 == 0 && ld >= V, "m3p_cross_entropy_fwd: pitch must be a multiple of 8 and >= V");
   M3P_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), stream));
   ce_count_kernel<<<1, 256, 0, stream>>>(y, n, ignore_index, inv_count);
-  ce_row_kernel<<<(unsigned)n, EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, y, (int)V,
-                                                        ignore_index, inv_count, loss,
+  ce_fwd_kernel<<<(unsigned)n, EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, y, (int)V,
+                                                        ignore_index, inv_count, loss, lse);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_cross_entropy_bwd(const void* logits, int64_t ld, const int64_t* y, int64_t n, int64_t V,
+                                     int64_t ignore_index, const float* lse, const float* inv_count,
+                                     const float* grad_scale, void* dlogits, int64_t ldd, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(logits && y && lse && inv_count && dlogits, "m3p_cross_entropy_bwd: null pointer");
+  M3P_REQUIRE(n > 0 && V > 0 && ld % 8 == 0 && ldd % 8 == 0 && ld >= V && ldd >= V,
+              "m3p_cross_entropy_bwd: pitches must be multiples of 8 and >= V");
+  ce_bwd_kernel<<<(unsigned)n, EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, y, (int)V,
+                                                        ignore_index, lse, inv_count, grad_scale,
                                                         reinterpret_cast<__nv_bfloat16*>(dlogits), ldd);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
@@ -605,11 +664,12 @@ extern "C" int m3p_rowdot_fwd(const void* x, const float* w, const float* bias, 
 }
 
 extern "C" int m3p_rowdot_bwd(const float* dout, const void* x, const float* w, void* dx, float* dw, float* db,
-                              int64_t rows, int64_t d, m3p_stream_t stream_) {
+                              int64_t rows, int64_t d, int32_t tanh_grad, m3p_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   M3P_REQUIRE(dout && x && w && dx && dw && db && rows > 0 && d > 0, "m3p_rowdot_bwd: bad arguments");
   rowdot_bwd_kernel<<<(unsigned)((d + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, stream>>>(
-      dout, reinterpret_cast<const __nv_bfloat16*>(x), w, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, rows, (int)d);
+      dout, reinterpret_cast<const __nv_bfloat16*>(x), w, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, rows, (int)d,
+      (int)tanh_grad);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }

@@ -113,10 +113,10 @@ if __name__ == "__main__":
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
     # C1 of BASELINE.json: 2 layers / 128 hidden, 16 text + 4 region tokens, batch 2
-    c1, keys = run_case("c1", 128, 2, 4, 1000, B=2, T=16, R=4, n_langs=1, ragged=False, seed=0)
+    c1, keys = run_case("c1", 128, 2, 2, 1000, B=2, T=16, R=4, n_langs=1, ragged=False, seed=0)
     torch.save(c1, os.path.join(gold, "c1_tiny.pt"))
     # ragged lengths + several languages (cross_lang_embeddings) + odd sizes
-    c1r, keys_r = run_case("c1_ragged", 128, 2, 4, 600, B=4, T=12, R=5, n_langs=3, ragged=True, seed=7)
+    c1r, keys_r = run_case("c1_ragged", 128, 2, 2, 600, B=4, T=12, R=5, n_langs=3, ragged=True, seed=7)
     torch.save(c1r, os.path.join(gold, "c1_ragged_langs.pt"))
     with open(os.path.join(gold, "state_dict_keys.json"), "w") as f:
         json.dump({"c1_tiny": keys, "c1_ragged_langs": keys_r}, f, indent=0, sort_keys=True)
