@@ -1,0 +1,310 @@
+"""Headline benchmark: image-text pairs/s, forward + backward, M3P-base (12L/768H/12 heads, 100 regions +
+128 tokens = 228-token joint sequence, bf16 tensor-core operands), 64 pairs per GPU (BASELINE.json
+configs[1]; data-parallel weak scaling for --gpus > 1, configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--heads itm|multitask] [--impl reference]
+
+One step = jointfwd + prediction head(s) + loss + backward through the reference-facing API
+(`model('jointfwd', ...)`, `model('predict', ...)`, `loss.backward()`), gradients zeroed and the bf16
+operand copies refreshed inside the timed region, plus the NCCL gradient all-reduce when N > 1.  The
+optimizer update is not part of the metric.  Prints ONE JSON line on rank 0.
+
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port of
+transformer.py / xtrainer.py under oracle/, fp32 PyTorch on all host cores) on a bounded sample of
+the same workload; it is the one place besides tests/ and smoke() that executes oracle/.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GF_PER_PAIR = {"itm": 122.886, "multitask": 143.356}  # BASELINE.md §3 (matmul FLOPs, fwd+bwd = 3x fwd)
+HEADS = {"itm": ("rel",), "multitask": ("mlm", "mrm", "mrfr", "rel")}
+CFG = dict(emb_dim=768, n_layers=12, n_heads=12, n_words=250002, T=128, R=100, sample_n=4, dropout=0.1)
+CPU_SAMPLE_PAIRS = 4
+
+
+def namespace(cfg, dropout=None):
+    return argparse.Namespace(
+        n_langs=1, n_words=cfg["n_words"], eos_index=2, pad_index=1, id2lang={0: "en"}, lang2id={"en": 0},
+        emb_dim=cfg["emb_dim"], n_heads=cfg["n_heads"], n_layers=cfg["n_layers"], n_dec_layers=cfg["n_layers"],
+        dropout=cfg["dropout"] if dropout is None else dropout,
+        attention_dropout=cfg["dropout"] if dropout is None else dropout, sinusoidal_embeddings=False,
+        refine_layers=1, attention_setting="v1", use_externel_att=False, gelu_activation=True, share_inout_emb=True,
+        asm=False)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(sustained=d.get("bf16_tflops_sustained", 1400.0), burst=d.get("bf16_tflops", 1590.0),
+                    hbm=d.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(sustained=1400.0, burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_pairs_per_s(heads, steps, warmup, threads=None):
+    """The reference algorithm on host cores: oracle/m3p_oracle.py (fp32 PyTorch restatement of
+    transformer.py + xtrainer.py loss assembly), full M3P-base weights, a B = 4 sample of the batch."""
+    import torch
+    from m3p_b200.transformer import TransformerModel
+    from m3p_b200.train_step import synthetic_batch
+    from oracle import m3p_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = TransformerModel(namespace(CFG, 0.0), is_encoder=True, with_output=True, is_crossModal=True)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+            if k.split(".")[0] in ("embeddings", "position_embeddings", "layer_norm_emb", "image_embeddings", "attentions",
+                                   "layer_norm1", "ffns", "layer_norm2", "pooled_layer", "seq_relationship", "mrfr_dense",
+                                   "transformer_obj", "pred_obj_layer") or k == "pred_layer.proj.bias"}
+    leaf["pred_layer.proj.weight"] = leaf["embeddings.weight"]
+    del model, sd
+    B = CPU_SAMPLE_PAIRS
+    batch = synthetic_batch(B, CFG["T"], CFG["R"], CFG["n_words"], sample_n=CFG["sample_n"], seed=1234)
+    times = []
+    for it in range(warmup + steps):
+        for v in leaf.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        _, _, total = O.pretrain_step_losses(leaf, CFG["n_layers"], CFG["n_heads"], batch, CFG["sample_n"], heads=heads)
+        total.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return B * len(times) / sum(times), threads, sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    heads = HEADS[args.heads]
+    v, threads, spt = cpu_reference_pairs_per_s(heads, args.steps, args.warmup)
+    sample = "%d pairs/step x %d steps, M3P-base fp32, oracle port on %d host threads" % (CPU_SAMPLE_PAIRS, args.steps, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": "image-text pairs/sec fwd+bwd, M3P-base 228-tok seq", "value": v, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.heads), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def workload_name(heads):
+    h = "ITM head (t2i/i2t fine-tune step)" if heads == "itm" else "xMLM-style MLM + MRM + MRFR + ITM heads (multitask step)"
+    return "M3P-base 12L/768H/12h jointfwd fwd+bwd, 100 regions + 128 tokens, 64 pairs/GPU, " + h
+
+
+def time_dominant_kernel(torch, ops, L):
+    """The FFN GEMM (M=14592, N=3072, K=768; 2/3 of the linear FLOPs are this shape or its transposes)
+    timed alone with CUDA events: the `roofline.dominant_kernel` entry."""
+    m, n, k = 14592, 3072, 768
+    a = torch.randn(m, k, device="cuda").to(torch.bfloat16)
+    w = torch.randn(n, k, device="cuda").to(torch.bfloat16)
+    bias = torch.randn(n, device="cuda")
+    out, out2 = torch.empty(m, n, device="cuda", dtype=torch.bfloat16), torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    times = []
+    for it in range(13):
+        flush.zero_()  # 256 MB > the 126 MB L2
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        ops.linear(a, w, bias, out, epi=L.M3P_EPI_GELU, out2=out2)
+        t1.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            times.append(t0.elapsed_time(t1))
+    ms = statistics.median(times)
+    return 2.0 * m * n * k / (ms * 1e-3) / 1e12, ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--heads", default="itm", choices=["itm", "multitask"])
+    ap.add_argument("--batch", type=int, default=64, help="pairs per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from m3p_b200 import lib as L, ops
+    from m3p_b200.ddp import GradReducer, init_distributed
+    from m3p_b200.train_step import pretrain_step, synthetic_batch
+    from m3p_b200.transformer import TransformerModel
+
+    rank, local, world = init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the M3P hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local)
+    ops.device_check()
+    heads = HEADS[args.heads]
+    B = args.batch
+    torch.manual_seed(0)
+    model = TransformerModel(namespace(CFG), is_encoder=True, with_output=True, is_crossModal=True).cuda().train()
+    reducer = GradReducer(model)
+    host = synthetic_batch(B, CFG["T"], CFG["R"], CFG["n_words"], sample_n=CFG["sample_n"], seed=1234 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    step_keys = ["x", "lengths", "x_img", "lengths_img", "image_loc", "pos_labels"]
+    if args.heads == "multitask":
+        step_keys += ["pred_mask_text", "y_text", "obj_labels", "ori_feats", "mrfr_weight"]
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in step_keys)
+
+    def step(batch):
+        model.zero_grad()
+        total, _ = pretrain_step(model, batch, CFG["sample_n"], heads)
+        total.backward()
+        reducer.finish()
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.LAUNCHES
+        t0.record()
+        for _ in range(n):
+            fn()
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, ops.LAUNCHES - l0
+
+    # ---- kernel-resident arm: inputs already in HBM ----
+    for _ in range(args.warmup):
+        step(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(lambda: step(resident), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end arm: pinned host inputs -> H2D -> step -> loss D2H, every step ----
+    def e2e_step():
+        b = dict(resident)
+        for k in step_keys:
+            b[k] = host[k].to(dev, non_blocking=True)
+        return float(step(b).detach())  # device -> host read of the loss
+
+    for _ in range(3):
+        e2e_step()
+    ms_e2e, _ = timed(e2e_step, args.steps)
+
+    pairs = B * world * args.steps
+    value = pairs / (ms * 1e-3)
+    e2e = pairs / (ms_e2e * 1e-3)
+    pk = peaks()
+    gf = GF_PER_PAIR[args.heads]
+    achieved = value * gf / 1e3 / world  # TFLOP/s per GPU
+    out = None
+    if rank == 0:
+        dom_tf, dom_ms = time_dominant_kernel(torch, ops, L)
+        out = {
+            "metric": "image-text pairs/sec fwd+bwd, M3P-base 228-tok seq", "value": value, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(args.heads), "global_batch": B * world, "seq_len": CFG["T"] + CFG["R"],
+                       "parallelism": "dp%d" % world, "dropout": CFG["dropout"], "vocab": CFG["n_words"],
+                       "l2": "per-step working set (0.18 GB bf16 weights + >4 GB activations) >> 126 MB L2; no flush needed",
+                       "gflop_per_pair": gf},
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["sustained"], "traffic": None,
+                         "scope": "whole fwd+bwd step per GPU: pairs/s x %.3f GFLOP/pair (BASELINE.md §3) over the "
+                                  "sustained cuBLAS bf16 peak, %s" % (gf, pk["source"]),
+                         "dominant_kernel": {"name": "gemm_kernel<256, GELU> FFN lin1 14592x3072x768", "ms": dom_ms,
+                                             "achieved": dom_tf, "peak": pk["burst"], "frac": dom_tf / pk["burst"],
+                                             "note": "timed alone, L2 flushed, vs burst peak"}},
+        }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            del model
+            torch.cuda.empty_cache()
+            v, threads, _ = cpu_reference_pairs_per_s(heads, 3, 1)
+            out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                   "sample": "%d pairs/step x 3 steps after 1 warm-up, same M3P-base weights shape and batch "
+                                             "generator, fp32 oracle port (oracle/m3p_oracle.py)" % CPU_SAMPLE_PAIRS}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

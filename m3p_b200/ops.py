@@ -13,7 +13,13 @@ _byref = ctypes.byref
 _vp = ctypes.c_void_p
 
 
+LAUNCHES = 0  # kernels of libm3p_sm100.so enqueued by this process (every entry point is one kernel launch,
+              # m3p_cross_entropy_fwd two); bench.py reports the per-step delta as `gpu_launches`
+
+
 def _stream():
+    global LAUNCHES
+    LAUNCHES += 1
     return _vp(torch.cuda.current_stream().cuda_stream)
 
 
@@ -156,6 +162,8 @@ def scatter_rows(src, flat_idx, n_inner, stride_outer, stride_inner, dst, n, d):
 
 
 def cross_entropy_fwd(logits, y, V, ignore_index, loss, lse, inv_count):
+    global LAUNCHES
+    LAUNCHES += 1
     L.check(_lib().m3p_cross_entropy_fwd(logits.data_ptr(), logits.stride(0), y.data_ptr(), logits.shape[0], V,
                                          ignore_index, loss.data_ptr(), lse.data_ptr(), inv_count.data_ptr(),
                                          _stream()), "m3p_cross_entropy_fwd")

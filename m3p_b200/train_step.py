@@ -1,0 +1,116 @@
+"""The trainer-side step that drives the hot path, restated from the reference trainer (which cannot
+be imported: it needs apex): `XTrainer.pretrain_under_step` (M3P/src/xtrainer.py:2234-2402),
+`t2i_step`/`i2t_step` (:1888-2018) and `get_mask_` (:2226-2232), with the host syncs removed
+(`.item()`, `.cpu().numpy()`, CPU-side ITM loss at :2367-2370 all stay on the device).
+
+Batches are dicts shaped like `retrieval_pretrain_collate` output (xtrainer.py:960-1045):
+  x (T,B) int64, lengths (B,), x_img (R,B,2048) fp32, lengths_img (B,), image_loc (R,B,5) fp32,
+  x_labels (T,B) int64 (-1 = not masked), obj_labels (B,R) int64 (-1 = not masked),
+  ori_feats (B,R,2048) fp32, pos_labels (B/sample_n,) int64.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def get_mask_(labels):
+    """xtrainer.py:2226-2232 — host-side batch preparation (boolean indexing syncs; do it once per batch)."""
+    return labels[labels > 0], labels != -1
+
+
+def prepare_batch(batch):
+    """Adds the derived tensors the step needs (`y_text`, `pred_mask_text`, `mrfr_weight`) so the step
+    itself never synchronises with the host."""
+    b = dict(batch)
+    if "x_labels" in b and "y_text" not in b:
+        b["y_text"], b["pred_mask_text"] = get_mask_(b["x_labels"])
+    if "obj_labels" in b and "mrfr_weight" not in b:
+        sel = (b["obj_labels"].reshape(-1) != -1).to(torch.float32)
+        b["mrfr_weight"] = sel / (sel.sum().clamp_min(1.0) * 2048.0)
+    return b
+
+
+def relation_loss(scores, pos_labels, sample_n, w_multi=1.0, w_bin=1.0):
+    """xtrainer.py:2359-2372 / 1917-1942: CE over groups of sample_n + BCE against the one-hot positive."""
+    ce = F.cross_entropy(scores.view(-1, sample_n), pos_labels)
+    onehot = F.one_hot(pos_labels, sample_n).to(scores.dtype)
+    bce = F.binary_cross_entropy_with_logits(scores.view(-1), onehot.view(-1))
+    return w_multi * ce + w_bin * bce
+
+
+def pretrain_step(model, batch, sample_n=4, heads=("mlm", "mrm", "mrfr", "rel"), lambdas=None):
+    """jointfwd + the selected heads + loss assembly (xtrainer.py:2281-2375).  `heads=("rel",)` is the
+    fine-tune ITM step (t2i_step / i2t_step, :1911-1942).  Returns (total_loss, dict of losses)."""
+    lam = dict(mlm=1.0, mrm=1.0, mrfr=1.0, rel=1.0)
+    if lambdas:
+        lam.update(lambdas)
+    R = batch["x_img"].shape[0]
+    enc = model("jointfwd", x=batch["x"], lengths=batch["lengths"], x_img=batch["x_img"],
+                lengths_img=batch["lengths_img"], causal=False, langs=None, image_loc=batch["image_loc"],
+                refine_image=False)
+    text_out = enc[R:]                     # :2287-2289
+    img_out = enc[:R].transpose(0, 1)
+    losses = {}
+    total = None
+
+    def add(name, value):
+        nonlocal total
+        losses[name] = value
+        total = lam[name] * value if total is None else total + lam[name] * value
+
+    if "mlm" in heads:
+        _, l = model("predict", tensor=text_out, pred_mask=batch["pred_mask_text"], y=batch["y_text"], get_scores=False)
+        add("mlm", l)
+    if "mrm" in heads:
+        _, l = model("predict", tensor=img_out, pred_mask=None, y=batch["obj_labels"].reshape(-1), get_scores=False,
+                     is_obj=True)
+        add("mrm", l)
+    if "mrfr" in heads:
+        reg = model("predict", tensor=img_out, is_mrfr=True)
+        diff = reg.reshape(-1, 2048).float() - batch["ori_feats"].reshape(-1, 2048)
+        # == F.mse_loss(reg[sel], target[sel]) (:2334-2348) without the boolean gather
+        add("mrfr", (diff * diff * batch["mrfr_weight"][:, None]).sum())
+    if "rel" in heads:
+        scores = model("predict", tensor=enc.transpose(0, 1), is_relation=True)
+        add("rel", relation_loss(scores, batch["pos_labels"], sample_n))
+    return total, losses
+
+
+def synthetic_batch(B, T, R, n_words, sample_n=4, seed=1234, ragged=False, n_mask_text=16, n_mask_img=16,
+                    device="cpu", feat_dim=2048):
+    """Seeded synthetic batch in the layout and value distributions of the reference pipeline
+    (SURVEY.md §8d): unit-L2 region features (dataset_pretrain.py:287,379), normalised 5-d boxes
+    (:298-300), <s>=0 / </s>=2 / <pad>=1 framing (xtrainer.py:829-880), masked regions zeroed (:258-292)."""
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.full((B,), T, dtype=torch.long)
+    if ragged:
+        lengths = torch.randint(max(4, T // 4), T + 1, (B,), generator=g)
+        lengths[0] = T
+    x = torch.randint(4, n_words - 2, (T, B), generator=g)
+    x[0] = 0
+    ar = torch.arange(T)[:, None]
+    x = torch.where(ar == (lengths - 1)[None, :], torch.full_like(x, 2), x)
+    x = torch.where(ar >= lengths[None, :], torch.full_like(x, 1), x)
+    x_img = F.normalize(torch.randn(R, B, feat_dim, generator=g), dim=-1)
+    loc = torch.rand(R, B, 5, generator=g)
+    image_loc = loc / loc.norm(dim=-1, keepdim=True)
+    lengths_img = torch.full((B,), R, dtype=torch.long)
+    ori_feats = x_img.transpose(0, 1).clone()
+    x_labels = torch.full((T, B), -1, dtype=torch.long)
+    obj_labels = torch.full((B, R), -1, dtype=torch.long)
+    for b in range(B):
+        n_valid = int(lengths[b]) - 2
+        k = min(n_mask_text, max(n_valid, 0))
+        if k > 0:
+            pos = torch.randperm(n_valid, generator=g)[:k] + 1
+            x_labels[pos, b] = torch.randint(4, n_words - 2, (k,), generator=g)
+        posi = torch.randperm(R, generator=g)[:min(n_mask_img, R)]
+        obj_labels[b, posi] = torch.randint(1, 1600, (len(posi),), generator=g)
+        x_img[posi, b] = 0.0
+    assert B % sample_n == 0
+    pos_labels = torch.randint(0, sample_n, (B // sample_n,), generator=g)
+    batch = dict(x=x, lengths=lengths, x_img=x_img, lengths_img=lengths_img, image_loc=image_loc, x_labels=x_labels,
+                 obj_labels=obj_labels, ori_feats=ori_feats, pos_labels=pos_labels)
+    batch = prepare_batch(batch)
+    if device != "cpu":
+        batch = {k: v.to(device) for k, v in batch.items()}
+    return batch

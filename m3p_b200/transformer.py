@@ -106,6 +106,7 @@ class TransformerModel(nn.Module):
                                       "got %d" % (self.dim // self.n_heads))
         self._seed_base = 0x5DEECE66D
         self._step = 0
+        self._grad_ready_hook = None  # set by ddp.GradReducer: (name, lo, hi) slice of _flat_grad is final
         self._build_parameters()
 
     # ------------------------------------------------------------------------------------------
@@ -191,6 +192,13 @@ class TransformerModel(nn.Module):
             self._hot_off[n] = off
             off += _align(int(math.prod(s)))
         self._flat_numel = off
+        # contiguous slices of the flat buffers, in the order the backward finishes them
+        first_layer = self._hot_off["attentions.0.q_lin.weight"] if self.n_layers > 0 else self._hot_off["pooled_layer.dense.weight"]
+        heads_lo = self._hot_off["pooled_layer.dense.weight"]
+        self._segments = {"embed": (0, first_layer), "heads": (heads_lo, off)}
+        for i in range(self.n_layers):
+            hi = self._hot_off["attentions.%d.q_lin.weight" % (i + 1)] if i + 1 < self.n_layers else heads_lo
+            self._segments["layer%d" % i] = (self._hot_off["attentions.%d.q_lin.weight" % i], hi)
         flat = torch.zeros(off, dtype=_F32)
         with torch.no_grad():
             for n, s, kind in spec:
@@ -586,6 +594,9 @@ class TransformerModel(nn.Module):
         p_drop, p_att, seqlen = st["p_drop"], st["p_att"], st["seqlen"]
         e = lambda *s, dt=_BF16: torch.empty(*s, dtype=dt, device=dev)
         scale = 1.0 / math.sqrt(d // H)
+        hook = self._grad_ready_hook
+        if hook is not None:
+            hook("heads", *self._segments["heads"])  # head backward ran before the encoder's
         for i in reversed(range(self.n_layers)):
             w, gr, s = self._layer_views(i), self._layer_grads(i), st["layers"][i]
             # layer_norm2 (+ row mask) and the FFN dropout           (:956-958, :226)
@@ -625,6 +636,8 @@ class TransformerModel(nn.Module):
             ops.colsum(dqkv, gr["bqkv"])
             dh = dhp
             st["layers"][i] = None
+            if hook is not None:
+                hook("layer%d" % i, *self._segments["layer%d" % i])
         # ---- embedding stage ----
         spec = st["spec"]
         flags = spec["flags"]
@@ -673,6 +686,8 @@ class TransformerModel(nn.Module):
                 dxi = e(B * R, FEAT_DIM)
                 ops.dgrad(de, self._w16("image_embeddings.image_embeddings.weight"), dxi)
                 d_ximg = dxi.view(B, R, FEAT_DIM).transpose(0, 1).to(_F32)
+        if hook is not None:
+            hook("embed", *self._segments["embed"])
         return d_ximg, d_text
 
 

@@ -1,0 +1,80 @@
+"""World-size-2 test of the data-parallel gradient exchange on CPU (gloo): the hook-driven, per-segment
+all-reduce of m3p_b200/ddp.py averages every slice exactly once, with and without overlap."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+class _FakeModel:
+    """Just the attributes GradReducer touches (the real model needs a B200)."""
+
+    def __init__(self, rank):
+        self._flat_grad = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        self._emb_grad = torch.full((50, 8), float(rank + 1))
+        self._proj_grad = self._emb_grad
+        self._grad_ready_hook = None
+        self._segments = {"embed": (0, 100), "layer0": (100, 400), "layer1": (400, 700), "heads": (700, 1000)}
+
+
+def _worker(rank, world, port, overlap, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from m3p_b200.ddp import GradReducer
+    m = _FakeModel(rank)
+    red = GradReducer(m, overlap=overlap)
+    assert m._grad_ready_hook is not None
+    # the order the backward announces them: heads, last layer ... first layer; "embed" is left to finish()
+    for name in ("heads", "layer1", "layer0"):
+        m._grad_ready_hook(name, *m._segments[name])
+    m._grad_ready_hook("layer0", *m._segments["layer0"])  # announcing twice must not reduce twice
+    red.finish()
+    want = torch.arange(1000, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    ok = torch.allclose(m._flat_grad, want) and torch.allclose(m._emb_grad, torch.full((50, 8), (world + 1) / 2))
+    # a second step reuses the reducer
+    m._flat_grad.fill_(float(rank))
+    red.finish()
+    ok = ok and torch.allclose(m._flat_grad, torch.full((1000,), (world - 1) / 2))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(overlap):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, overlap, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
+
+def test_overlapped_segment_allreduce_world2():
+    _run(True)
+
+
+def test_end_of_backward_allreduce_world2():
+    _run(False)
+
+
+def test_single_process_is_a_noop():
+    from m3p_b200.ddp import GradReducer
+    m = _FakeModel(0)
+    before = m._flat_grad.clone()
+    red = GradReducer(m)
+    assert m._grad_ready_hook is None
+    red.finish()
+    assert torch.equal(m._flat_grad, before)

@@ -232,10 +232,10 @@ def case_golden(name):
     ref = g["joint"]
     res = dict(case="golden/" + name, enc=_rel(enc.detach().cpu(), ref["enc"]))
     for k in ("mlm", "mrm", "mrfr", "rel"):
-        res["loss_" + k] = abs(float(losses[k]) - ref["losses"][k]) / abs(ref["losses"][k])
+        res["loss_" + k] = abs(float(losses[k].detach()) - ref["losses"][k]) / abs(ref["losses"][k])
     res["grad_x_img"] = _rel(batch["x_img"].grad.cpu(), ref["grad_x_img"])
     worst, worst_name = 0.0, ""
-    named = dict(model.named_parameters())
+    named = dict(model.named_parameters(remove_duplicate=False))
     for k, gr in ref["grads"].items():
         if k == "pred_layer.proj.weight":
             continue
@@ -279,7 +279,7 @@ def case_step(B, L_=12, d=768, H=12, V=250002, heads=("rel",), dropout=0.1, step
     ms = t0.elapsed_time(t1) / steps
     gn = float(model._flat_grad.norm())
     _out(case="step", B=B, L=L_, d=d, heads=list(heads), dropout=dropout, ms_per_step=ms, pairs_per_s=B / ms * 1e3,
-         loss=float(total), grad_norm=gn, finite=math.isfinite(gn) and math.isfinite(float(total)),
+         loss=float(total.detach()), grad_norm=gn, finite=math.isfinite(gn) and math.isfinite(float(total.detach())),
          mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, ok=math.isfinite(gn))
 
 
