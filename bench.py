@@ -57,11 +57,18 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -70,7 +77,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -81,7 +88,9 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.t0 is not None and not (self.t0 <= ts <= (self.t1 or ts)):
+                continue  # only samples taken DURING the timed region
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -175,7 +184,7 @@ def time_dominant_kernel(torch, ops, L):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--heads", default="itm", choices=["itm", "multitask"])
@@ -240,12 +249,14 @@ def main():
         return ms, ops.LAUNCHES - l0
 
     # ---- kernel-resident arm: inputs already in HBM ----
-    for _ in range(args.warmup):
-        step(resident)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # nvidia-smi takes a moment to start: launch it before the warm-up
+    for _ in range(args.warmup):
+        step(resident)
+    sampler.mark_begin()
     ms, launches = timed(lambda: step(resident), args.steps)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end arm: pinned host inputs -> H2D -> step -> loss D2H, every step ----

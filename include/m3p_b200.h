@@ -57,9 +57,9 @@ M3P_API int m3p_device_check(void);
  *   heads :104-117, 576-584, 602-606, 1195-1204.
  * Epilogues (v = alpha * acc + bias[n]):
  *   M3P_EPI_LINEAR   out = v                                   (bf16 or fp32; fp32 may accumulate)
- *   M3P_EPI_GELU     out = v (pre-activation), out2 = gelu_erf(v)          transformer.py:48-56,224
+ *   M3P_EPI_GELU     out2 = gelu_erf(v), out = gelu_erf'(v) (stash for bwd)   transformer.py:48-56,224
  *   M3P_EPI_DROP_RES out = aux + dropout(v)        (aux = residual)        transformer.py:951-952,956
- *   M3P_EPI_DGELU    out = v * gelu_erf'(aux)      (aux = pre-activation; backward of :224)
+ *   M3P_EPI_DGELU    out = v * aux                 (aux = the stashed gelu_erf'; backward of :224)
  *   M3P_EPI_TANH     out = tanh(v)                                          transformer.py:556-557
  *   M3P_EPI_DTANH    out = v * (1 - aux^2)         (aux = tanh output; backward of :557)
  * split_k > 1 requires out_f32 = 1 and accumulate = 1 (partial sums are reduced with red.add).
@@ -175,9 +175,10 @@ M3P_API int m3p_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows,
 
 /* out = bf16(scale * in): refreshes the bf16 tensor-core copies of the fp32 master parameters. */
 M3P_API int m3p_cast_f32_bf16(const float* in, void* out, int64_t n, float scale, m3p_stream_t stream);
-/* du = dg * gelu_erf'(u), bf16: backward of the activation of BertPredictionHeadTransform
- * (transformer.py:603-604; the FFN's GELU backward is fused into a GEMM epilogue instead). */
-M3P_API int m3p_gelu_bwd(const void* dg, const void* u, void* du, int64_t n, m3p_stream_t stream);
+/* du = dg * gp, bf16, gp = gelu_erf'(u) as stashed by the M3P_EPI_GELU epilogue: backward of the
+ * activation of BertPredictionHeadTransform (transformer.py:603-604; the FFN's GELU backward is fused
+ * into a GEMM epilogue instead). */
+M3P_API int m3p_gelu_bwd(const void* dg, const void* gp, void* du, int64_t n, m3p_stream_t stream);
 /* (A,B,F) fp32 -> (B,A,F) bf16: the reference's sequence-first inputs (x_img (R,bs,2048),
  * transformer.py:895) to batch-major GEMM rows. */
 M3P_API int m3p_permute_cast_f32_bf16(const float* in, void* out, int64_t A, int64_t B, int64_t F,

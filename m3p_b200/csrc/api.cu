@@ -36,6 +36,29 @@ int sm_count() {
   return n;
 }
 
+float* scratch_f32(size_t n_floats) {
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (n_floats > cap) {
+    size_t want = n_floats < (size_t(4) << 20) ? (size_t(4) << 20) : n_floats * 2;
+    if (buf != nullptr) {
+      cudaDeviceSynchronize();
+      cudaFree(buf);
+      buf = nullptr;
+      cap = 0;
+    }
+    if (cudaMalloc(&buf, want * sizeof(float)) != cudaSuccess) {
+      set_last_error("scratch allocation of %zu bytes failed", want * sizeof(float));
+      buf = nullptr;
+      return nullptr;
+    }
+    cap = want;
+  }
+  return buf;
+}
+
 // ---- tensor-map cache ------------------------------------------------------------------------
 struct TmapKey {
   uint64_t v[10];

@@ -39,6 +39,13 @@ int get_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t 
                      uint64_t dim2, uint64_t pitch1, uint64_t pitch2, uint32_t box0, uint32_t box1,
                      uint32_t box2);
 int sm_count();
+// Library-owned scratch for cross-CTA partial sums (column reductions of LayerNorm / bias gradients):
+// one buffer per process (= per GPU), grown on demand, reused by every call on the stream.  Many CTAs
+// adding atomically into the same few thousand addresses serialise in L2 (~250 cycles per same-address
+// op measured on B200), so reductions go partials -> scratch -> one small second-stage kernel instead.
+float* scratch_f32(size_t n_floats);
+// out_k[col] += sum_p partial[p][k * seg + col]  for k < nout; second stage of the reductions above.
+int reduce_partials(const float* partial, int parts, int seg, float* const* outs, int nout, cudaStream_t stream);
 
 // ---- dropout generator -------------------------------------------------------------------------
 // One 32-bit hash per PAIR of consecutive elements; each 16-bit half decides one element:

@@ -48,6 +48,40 @@ static int ew_grid(long long rows) {
 }
 
 // =================================================================================================
+// second stage of the column reductions: out_k[col] += sum_p partial[p][k*seg + col]
+// =================================================================================================
+struct ReduceOuts { float* p[4]; };
+__global__ void __launch_bounds__(EW_THREADS)
+reduce_partials_kernel(const float* __restrict__ partial, int parts, int seg, int ncols, ReduceOuts outs) {
+  const int col = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (col >= ncols) return;
+  float* dst = outs.p[col / seg];
+  if (dst == nullptr) return;
+  float acc = 0.f;
+  int p = blockIdx.y;
+  const int step = gridDim.y;
+  for (; p + 3 * step < parts; p += 4 * step) {
+    const float a = partial[(long long)p * ncols + col], b = partial[(long long)(p + step) * ncols + col];
+    const float c = partial[(long long)(p + 2 * step) * ncols + col], e = partial[(long long)(p + 3 * step) * ncols + col];
+    acc += (a + b) + (c + e);
+  }
+  for (; p < parts; p += step) acc += partial[(long long)p * ncols + col];
+  atomicAdd(dst + (col % seg), acc);  // gridDim.y-way contention only
+}
+
+int reduce_partials(const float* partial, int parts, int seg, float* const* outs, int nout, cudaStream_t stream) {
+  ReduceOuts o{};
+  for (int i = 0; i < nout && i < 4; ++i) o.p[i] = outs[i];
+  const int ncols = seg * nout;
+  int gy = parts / 16;
+  gy = gy < 1 ? 1 : (gy > 8 ? 8 : gy);
+  reduce_partials_kernel<<<dim3((ncols + EW_THREADS - 1) / EW_THREADS, gy), EW_THREADS, 0, stream>>>(partial, parts, seg,
+                                                                                                   ncols, o);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+// =================================================================================================
 // LayerNorm forward:  y = mask * ((x - mean) * rstd * gamma + beta)      transformer.py:953,957-958
 // =================================================================================================
 template <int MAXC>
@@ -117,16 +151,15 @@ struct LnBwdParams {
   uint32_t dx_thr16, dx_seed_lo, dx_seed_hi; float dx_scale;
   uint32_t dy_thr16, dy_seed_lo, dy_seed_hi; float dy_scale;
   float* dgamma; float* dbeta; float* dbias;
+  float* partial;  // [gridDim.x][3][d] scratch: per-CTA column sums (dgamma | dbeta | dbias)
   long long rows; int d;
 };
 
 template <typename XT, typename DYT, typename DXT, int MAXC>
 __global__ void __launch_bounds__(EW_THREADS)
 ln_bwd_kernel(const LnBwdParams p) {
-  extern __shared__ float sacc[];  // [3][d]
+  extern __shared__ float sacc[];  // [EW_WARPS][MAXC * 8 * 32]
   const int d = p.d;
-  for (int i = threadIdx.x; i < 3 * d; i += EW_THREADS) sacc[i] = 0.f;
-  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * EW_WARPS;
@@ -194,35 +227,49 @@ ln_bwd_kernel(const LnBwdParams p) {
       }
     }
   }
-  // block reduction through shared memory, then one global atomic per column per CTA
+  // cross-warp reduction: every warp owns the same (lane -> columns) map, so partials are laid out
+  // [warp][slot][lane] (conflict-free), summed over warps, then one global atomic per column per CTA
+  const int warp = threadIdx.x >> 5;
+  constexpr int SLOTS = MAXC * 8 * 32;
+  auto reduce_one = [&](float (&acc)[MAXC][8], const float* wanted, int which) {
+    if (wanted == nullptr) return;  // uniform across the CTA
+    float* dst = p.partial + ((long long)blockIdx.x * 3 + which) * d;
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
-    const int ch = lane + 32 * c;
-    if (ch < nchunks) {
+    for (int c = 0; c < MAXC; ++c)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sacc[ch * 8 + j], acc_g[c][j]);
-        atomicAdd(&sacc[d + ch * 8 + j], acc_b[c][j]);
-        if (p.dbias != nullptr) atomicAdd(&sacc[2 * d + ch * 8 + j], acc_bias[c][j]);
-      }
+      for (int j = 0; j < 8; ++j) sacc[warp * SLOTS + (c * 8 + j) * 32 + lane] = acc[c][j];
+    __syncthreads();
+    for (int slot = threadIdx.x; slot < SLOTS; slot += EW_THREADS) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < EW_WARPS; ++w) sum += sacc[w * SLOTS + slot];
+      const int k = slot >> 5, l = slot & 31;
+      const int ch = l + 32 * (k >> 3);
+      if (ch < nchunks) dst[ch * 8 + (k & 7)] = sum;
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < d; i += EW_THREADS) {
-    if (p.dgamma != nullptr) atomicAdd(p.dgamma + i, sacc[i]);
-    if (p.dbeta != nullptr) atomicAdd(p.dbeta + i, sacc[d + i]);
-    if (p.dbias != nullptr) atomicAdd(p.dbias + i, sacc[2 * d + i]);
-  }
+    __syncthreads();
+  };
+  reduce_one(acc_g, p.dgamma, 0);
+  reduce_one(acc_b, p.dbeta, 1);
+  reduce_one(acc_bias, p.dbias, 2);
 }
 
 template <typename XT, typename DYT, typename DXT>
-static int launch_ln_bwd(const LnBwdParams& p, cudaStream_t stream) {
-  const int grid = ew_grid(p.rows) < sm_count() * 2 ? ew_grid(p.rows) : sm_count() * 2;
-  const size_t smem = 3 * p.d * sizeof(float);
-  if (p.d <= 256) ln_bwd_kernel<XT, DYT, DXT, 1><<<grid, EW_THREADS, smem, stream>>>(p);
-  else if (p.d <= 768) ln_bwd_kernel<XT, DYT, DXT, 3><<<grid, EW_THREADS, smem, stream>>>(p);
-  else ln_bwd_kernel<XT, DYT, DXT, 4><<<grid, EW_THREADS, smem, stream>>>(p);
+static int launch_ln_bwd(LnBwdParams p, cudaStream_t stream) {
+  // one CTA per SM (the kernel is register-heavy: 1 CTA / SM), every warp streams rows; the per-CTA
+  // column sums go to scratch and are folded by reduce_partials (no same-address atomics storm)
+  long long need = (p.rows + EW_WARPS - 1) / EW_WARPS;
+  const long long cap = (long long)sm_count() * 2;
+  const int grid = (int)(need < cap ? need : cap);
+  p.partial = scratch_f32((size_t)grid * 3 * p.d);
+  if (p.partial == nullptr) return M3P_ERR_CUDA;
+  auto smem = [](int maxc) { return (size_t)EW_WARPS * maxc * 8 * 32 * sizeof(float); };
+  if (p.d <= 256) ln_bwd_kernel<XT, DYT, DXT, 1><<<grid, EW_THREADS, smem(1), stream>>>(p);
+  else if (p.d <= 768) ln_bwd_kernel<XT, DYT, DXT, 3><<<grid, EW_THREADS, smem(3), stream>>>(p);
+  else ln_bwd_kernel<XT, DYT, DXT, 4><<<grid, EW_THREADS, smem(4), stream>>>(p);
   M3P_CUDA_OK(cudaGetLastError());
+  float* outs[3] = {p.dgamma, p.dbeta, p.dbias};
+  if (p.dgamma || p.dbeta || p.dbias) return reduce_partials(p.partial, grid, p.d, outs, 3, stream);
   return M3P_OK;
 }
 
@@ -230,22 +277,35 @@ static int launch_ln_bwd(const LnBwdParams& p, cudaStream_t stream) {
 // column sums (bias gradients): out[j] += sum_rows x[row][j]
 // =================================================================================================
 __global__ void __launch_bounds__(EW_THREADS)
-colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, long long rows, int n,
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ partial, long long rows, int n,
               long long rows_per_cta) {
-  // thread owns 8 consecutive columns of a 2048-column stripe; CTA walks its row range
+  // thread owns 8 consecutive columns (one 16-byte vector) of a 2048-column stripe; the CTA walks its
+  // row range 8 rows at a time so 8 independent 16-byte loads per thread are in flight
   const int col0 = (blockIdx.y * EW_THREADS + threadIdx.x) * 8;
   if (col0 >= n) return;
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long r = r0; r < r1; ++r) {
+  long long r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    uint4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const uint4*>(x + (r + i) * ld + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0] += bf16_lo(t[i].x); acc[1] += bf16_hi(t[i].x); acc[2] += bf16_lo(t[i].y); acc[3] += bf16_hi(t[i].y);
+      acc[4] += bf16_lo(t[i].z); acc[5] += bf16_hi(t[i].z); acc[6] += bf16_lo(t[i].w); acc[7] += bf16_hi(t[i].w);
+    }
+  }
+  for (; r < r1; ++r) {
     float v[8];
     load8(x + r * ld + col0, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += v[j];
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(out + col0 + j, acc[j]);
+  float* dst = partial + (long long)blockIdx.x * n + col0;
+  *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
 // =================================================================================================
@@ -278,8 +338,9 @@ permute_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ ou
   }
 }
 
-// du = dg * gelu_erf'(u): backward of the GELU inside BertPredictionHeadTransform (transformer.py:603-604),
-// where the LayerNorm backward sits between the next linear's dgrad and this activation.
+// du = dg * gp (gp = gelu_erf'(u) stashed by the forward GEMM epilogue): backward of the GELU inside
+// BertPredictionHeadTransform (transformer.py:603-604), where the LayerNorm backward sits between the
+// next linear's dgrad and this activation.
 __global__ void __launch_bounds__(EW_THREADS)
 gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dg, const __nv_bfloat16* __restrict__ u,
                 __nv_bfloat16* __restrict__ du, long long n8) {
@@ -289,7 +350,7 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dg, const __nv_bfloat16* __res
     load8(dg + i * 8, a);
     load8(u + i * 8, b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] *= gelu_erf_grad(b[j]);
+    for (int j = 0; j < 8; ++j) a[j] *= b[j];
     store8(du + i * 8, a);
   }
 }
@@ -332,16 +393,30 @@ scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, const int64_t* __rest
 //   transformer.py:112 (MLM), :581 (MRM).  One CTA per row.
 //   loss += -(logit[y] - lse) / n_valid ;  dlogits = (softmax - onehot) / n_valid   (0 for ignored rows)
 // =================================================================================================
-__global__ void ce_count_kernel(const int64_t* __restrict__ y, long long n, long long ignore_index,
-                                float* __restrict__ inv_count) {
-  __shared__ int s_cnt;
-  if (threadIdx.x == 0) s_cnt = 0;
+// *loss = mean over non-ignored rows of row_loss ; *inv_count = 1 / #non-ignored rows   (one CTA: a
+// thousand CTAs adding into one address would serialise in L2)
+__global__ void ce_finish_kernel(const float* __restrict__ row_loss, const int64_t* __restrict__ y, long long n,
+                                 long long ignore_index, float* __restrict__ loss, float* __restrict__ inv_count) {
+  __shared__ float s_sum[32];
+  __shared__ int s_cnt[32];
+  float sum = 0.f;
+  int cnt = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    if (y[i] != ignore_index) { cnt += 1; sum += row_loss[i]; }
+  }
+  sum = warp_sum(sum);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_cnt[threadIdx.x >> 5] = cnt; }
   __syncthreads();
-  int c = 0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) c += (y[i] != ignore_index) ? 1 : 0;
-  atomicAdd(&s_cnt, c);
-  __syncthreads();
-  if (threadIdx.x == 0) *inv_count = s_cnt > 0 ? 1.0f / (float)s_cnt : 0.f;  // 0 valid rows: torch gives nan; we give 0 grads
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    int c = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t += s_sum[w]; c += s_cnt[w]; }
+    // 0 valid rows: torch gives nan; we give loss 0 and zero gradients
+    *inv_count = c > 0 ? 1.0f / (float)c : 0.f;
+    *loss = c > 0 ? t / (float)c : 0.f;
+  }
 }
 
 // (m, s) <- combine((m, s), (m2, s2)) for the online log-sum-exp
@@ -353,8 +428,7 @@ __device__ __forceinline__ void lse_combine(float& m, float& s, float m2, float 
 
 __global__ void __launch_bounds__(EW_THREADS)
 ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const int64_t* __restrict__ y, int V,
-              long long ignore_index, const float* __restrict__ inv_count, float* __restrict__ loss,
-              float* __restrict__ lse_out) {
+              long long ignore_index, float* __restrict__ row_loss, float* __restrict__ lse_out) {
   __shared__ float s_m[EW_WARPS], s_s[EW_WARPS];
   const long long row = blockIdx.x;
   const __nv_bfloat16* lp = logits + row * ld;
@@ -394,7 +468,7 @@ ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const int6
     for (int w = 1; w < EW_WARPS; ++w) lse_combine(m, s, s_m[w], s_s[w]);
     const float lse = m + logf(s);
     lse_out[row] = lse;
-    atomicAdd(loss, (lse - __bfloat162float(lp[target])) * (*inv_count));
+    row_loss[row] = lse - __bfloat162float(lp[target]);
   }
 }
 
@@ -550,13 +624,17 @@ extern "C" int m3p_colsum_bf16(const void* x, int64_t ld, float* out, int64_t ro
   const int gy = (int)((n / 8 + EW_THREADS - 1) / EW_THREADS);
   int gx = sm_count() * 4 / gy;
   if (gx < 1) gx = 1;
-  if (gx > rows) gx = (int)rows;
-  const long long rpc = (rows + gx - 1) / gx;
+  long long rpc = (rows + gx - 1) / gx;
+  rpc = (rpc + 7) / 8 * 8;  // whole 8-row batches
+  if (rpc < 16) rpc = 16;
   gx = (int)((rows + rpc - 1) / rpc);
-  colsum_kernel<<<dim3(gx, gy), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, out, rows,
+  float* partial = scratch_f32((size_t)gx * n);
+  if (partial == nullptr) return M3P_ERR_CUDA;
+  colsum_kernel<<<dim3(gx, gy), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, partial, rows,
                                                         (int)n, rpc);
   M3P_CUDA_OK(cudaGetLastError());
-  return M3P_OK;
+  float* outs[1] = {out};
+  return reduce_partials(partial, gx, (int)n, outs, 1, stream);
 }
 
 extern "C" int m3p_cast_f32_bf16(const float* in, void* out, int64_t n, float scale, m3p_stream_t stream_) {
@@ -631,10 +709,11 @@ extern "C" int m3p_cross_entropy_fwd(const void* logits, int64_t ld, const int64
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   M3P_REQUIRE(logits && y && loss && lse && inv_count, "m3p_cross_entropy_fwd: null pointer");
   M3P_REQUIRE(n > 0 && V > 0 && ld % 8 == 0 && ld >= V, "m3p_cross_entropy_fwd: pitch must be a multiple of 8 and >= V");
-  M3P_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), stream));
-  ce_count_kernel<<<1, 256, 0, stream>>>(y, n, ignore_index, inv_count);
+  float* row_loss = scratch_f32((size_t)n);
+  if (row_loss == nullptr) return M3P_ERR_CUDA;
   ce_fwd_kernel<<<(unsigned)n, EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, y, (int)V,
-                                                        ignore_index, inv_count, loss, lse);
+                                                        ignore_index, row_loss, lse);
+  ce_finish_kernel<<<1, 1024, 0, stream>>>(row_loss, y, n, ignore_index, loss, inv_count);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }

@@ -2,11 +2,13 @@
 //
 //   C[m][n] = sum_k A(m,k) * B(n,k)      bf16 operands, fp32 accumulation in TMEM
 //
-// Roles (256 threads / CTA, one CTA per SM):
+// Roles (384 threads / CTA, one CTA per SM):
 //   warp 0   TMA producer: cp.async.bulk.tensor tiles into a STAGES-deep 128B-swizzled smem ring
 //   warp 1   MMA issuer  : one elected thread issues tcgen05.mma (128 x BN x 16) and commits
 //   warp 2   TMEM allocator (2 accumulator stages of BN fp32 columns)
-//   warps 4-7 epilogue   : tcgen05.ld 32 columns at a time, fused math, vectorised global stores
+//   warps 4-11 epilogue  : tcgen05.ld 32 columns at a time, fused math, vectorised global stores;
+//                          two warps per TMEM lane quarter, each taking half of the tile's columns
+//                          (the erf-GELU / dropout epilogues are issue-bound with one warp per quarter)
 // Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), and the
 // static persistent tile loop, so the epilogue of tile i overlaps the main loop of tile i+1.
 //
@@ -21,7 +23,8 @@ namespace m3p {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
 constexpr uint32_t SLAB_BYTES = 64 * BLOCK_K * 2;  // one 64-wide MN slab of an MN-major tile
 
 struct GemmKernelParams {
@@ -53,18 +56,40 @@ __device__ __forceinline__ void decode_unit(const GemmKernelParams& p, int u, in
   m_tile = t / p.num_n_tiles;
 }
 
-// ---- epilogue math on one 32-column chunk held by one thread (one output row) -------------------
+// ---- epilogue math on one 16-column chunk held by one thread (one output row) -------------------
+// 16 columns = 32 bytes of bf16 per row: every global access of a thread is one full 32-byte sector.
+constexpr int EW = 16;  // epilogue chunk width (columns)
+
+__device__ __forceinline__ void load_bf16x16(const __nv_bfloat16* p, float* x) {
+  const uint4* a4 = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint4 t = __ldg(a4 + j);
+    x[8 * j + 0] = bf16_lo(t.x); x[8 * j + 1] = bf16_hi(t.x);
+    x[8 * j + 2] = bf16_lo(t.y); x[8 * j + 3] = bf16_hi(t.y);
+    x[8 * j + 4] = bf16_lo(t.z); x[8 * j + 5] = bf16_hi(t.z);
+    x[8 * j + 6] = bf16_lo(t.w); x[8 * j + 7] = bf16_hi(t.w);
+  }
+}
+__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* p, const float* v) {
+  uint4* o4 = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    o4[j] = make_uint4(pack_bf16x2(v[8 * j + 0], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+}
+
 template <int EPI, bool OUT_F32>
 __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const uint32_t* acc,
                                                long long row, int col0, int ncols) {
-  float v[32];
-  const bool full = (ncols == 32) && p.vec_ok;
+  float v[EW];
+  const bool full = (ncols == EW) && p.vec_ok;
   // v = alpha * acc + bias
   if (p.bias != nullptr) {
     if (full) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < EW / 4; ++j) {
         const float4 b = __ldg(b4 + j);
         v[4 * j + 0] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 0]), b.x);
         v[4 * j + 1] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 1]), b.y);
@@ -73,31 +98,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < EW; ++j)
         v[j] = fmaf(p.alpha, __uint_as_float(acc[j]), (j < ncols) ? __ldg(p.bias + col0 + j) : 0.f);
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(acc[j]);
+    for (int j = 0; j < EW; ++j) v[j] = p.alpha * __uint_as_float(acc[j]);
   }
 
-  // auxiliary operand (residual / pre-activation / tanh output)
+  // auxiliary operand (residual / stashed gelu' / tanh output)
   if constexpr (EPI == M3P_EPI_DROP_RES || EPI == M3P_EPI_DGELU || EPI == M3P_EPI_DTANH) {
-    float x[32];
+    float x[EW];
     const __nv_bfloat16* ap = p.aux + row * p.ldaux + col0;
     if (full) {
-      const uint4* a4 = reinterpret_cast<const uint4*>(ap);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 t = __ldg(a4 + j);
-        x[8 * j + 0] = bf16_lo(t.x); x[8 * j + 1] = bf16_hi(t.x);
-        x[8 * j + 2] = bf16_lo(t.y); x[8 * j + 3] = bf16_hi(t.y);
-        x[8 * j + 4] = bf16_lo(t.z); x[8 * j + 5] = bf16_hi(t.z);
-        x[8 * j + 6] = bf16_lo(t.w); x[8 * j + 7] = bf16_hi(t.w);
-      }
+      load_bf16x16(ap, x);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = (j < ncols) ? __bfloat162float(ap[j]) : 0.f;
+      for (int j = 0; j < EW; ++j) x[j] = (j < ncols) ? __bfloat162float(ap[j]) : 0.f;
     }
     if constexpr (EPI == M3P_EPI_DROP_RES) {
       if (p.thr16 != 0) {
@@ -105,30 +122,51 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
                             static_cast<uint32_t>(col0);
         if ((e0 & 1u) == 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < EW / 2; ++j) {
             const uint32_t h = drop_hash((e0 >> 1) + j, p.seed_lo, p.seed_hi);
             v[2 * j] = ((h & 0xffffu) >= p.thr16) ? v[2 * j] * p.drop_scale : 0.f;
             v[2 * j + 1] = ((h >> 16) >= p.thr16) ? v[2 * j + 1] * p.drop_scale : 0.f;
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < EW; ++j)
             v[j] = drop_keep(e0 + j, p.seed_lo, p.seed_hi, p.thr16) ? v[j] * p.drop_scale : 0.f;
         }
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += x[j];
+      for (int j = 0; j < EW; ++j) v[j] += x[j];
     } else if constexpr (EPI == M3P_EPI_DGELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(x[j]);
+      for (int j = 0; j < EW; ++j) v[j] *= x[j];  // x = gelu'(u) stashed by the forward epilogue
     } else {  // DTANH
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= (1.0f - x[j] * x[j]);
+      for (int j = 0; j < EW; ++j) v[j] *= (1.0f - x[j] * x[j]);
     }
   }
   if constexpr (EPI == M3P_EPI_TANH) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+    for (int j = 0; j < EW; ++j) v[j] = tanhf(v[j]);
+  }
+  if constexpr (EPI == M3P_EPI_GELU) {
+    // out2 = gelu(v), out = gelu'(v): one erf / exp evaluation serves both, and the backward
+    // (M3P_EPI_DGELU) becomes a plain multiply by the stashed derivative.
+    float gq[EW];
+#pragma unroll
+    for (int j = 0; j < EW; ++j) {
+      float e;
+      const float er = erf_as(v[j] * 0.70710678118654752f, &e);
+      const float cdf = fmaf(0.5f, er, 0.5f);
+      gq[j] = v[j] * cdf;
+      v[j] = fmaf(v[j] * e, 0.3989422804014327f, cdf);
+    }
+    __nv_bfloat16* gp = p.out2 + row * p.ldo2 + col0;
+    if (full) {
+      store_bf16x16(gp, gq);
+    } else {
+#pragma unroll
+      for (int j = 0; j < EW; ++j)
+        if (j < ncols) gp[j] = __float2bfloat16_rn(gq[j]);
+    }
   }
 
   // ---- stores ----
@@ -138,16 +176,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
       float4* o4 = reinterpret_cast<float4*>(op);
       if (p.accumulate) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < EW / 4; ++j)
           atomicAdd(o4 + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < EW / 4; ++j)
           o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < EW; ++j) {
         if (j < ncols) {
           if (p.accumulate) atomicAdd(op + j, v[j]);
           else op[j] = v[j];
@@ -157,33 +195,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
   } else {
     __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
     if (full) {
-      uint4* o4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        o4[j] = make_uint4(pack_bf16x2(v[8 * j + 0], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+      store_bf16x16(op, v);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < EW; ++j)
         if (j < ncols) op[j] = __float2bfloat16_rn(v[j]);
-    }
-    if constexpr (EPI == M3P_EPI_GELU) {
-      // second output: gelu of the bf16-ROUNDED pre-activation, so backward (which only sees the
-      // stored bf16 u) differentiates exactly the function forward evaluated.
-      __nv_bfloat16* gp = p.out2 + row * p.ldo2 + col0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__bfloat162float(__float2bfloat16_rn(v[j])));
-      if (full) {
-        uint4* g4 = reinterpret_cast<uint4*>(gp);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          g4[j] = make_uint4(pack_bf16x2(v[8 * j + 0], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) gp[j] = __float2bfloat16_rn(v[j]);
-      }
     }
   }
 }
@@ -228,7 +244,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], EPI_WARPS);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -311,7 +327,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
-    const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
+    const int q = warp_idx & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp_idx - 4) >> 2;  // which half of the tile's columns this warp drains
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
@@ -322,14 +339,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(t_base + c * 32, acc);
-        tmem_ld_wait();
-        if (row < p.M) epilogue_chunk<EPI, OUT_F32>(p, acc, row, col0, min(32, p.N - col0));
+      // software-pipelined drain: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed
+      constexpr int NCH = BN / 2 / EW;  // chunks per warp (this warp's half of the tile)
+      const int cbase = half * (BN / 2);
+      uint32_t acc[2][EW];
+      tmem_ld_32x32b_x16(t_base + cbase, acc[0]);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        tmem_ld_wait16(acc[i & 1]);
+        if (i + 1 < NCH) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[(i + 1) & 1]);
+        const int col0 = n0 + cbase + i * EW;
+        if (row < p.M && col0 < p.N)
+          epilogue_chunk<EPI, OUT_F32>(p, acc[i & 1], row, col0, min(EW, p.N - col0));
       }
       tc_fence_before();
       __syncwarp();

@@ -142,8 +142,8 @@ def cast_f32_bf16(src, dst, n=None, scale=1.0):
     L.check(_lib().m3p_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), n, scale, _stream()), "m3p_cast_f32_bf16")
 
 
-def gelu_bwd(dg, u, du):
-    L.check(_lib().m3p_gelu_bwd(dg.data_ptr(), u.data_ptr(), du.data_ptr(), u.numel(), _stream()), "m3p_gelu_bwd")
+def gelu_bwd(dg, gp, du):
+    L.check(_lib().m3p_gelu_bwd(dg.data_ptr(), gp.data_ptr(), du.data_ptr(), gp.numel(), _stream()), "m3p_gelu_bwd")
 
 
 def permute_cast(src, dst, A, B, F):

@@ -573,14 +573,14 @@ class TransformerModel(nn.Module):
             ops.linear(ctx, w["wo"], w["bo"], x1, epi=L.M3P_EPI_DROP_RES, aux=h, drop_p=p_drop, seed=s1)
             h1, mean1, rstd1 = e(M, d), e(M, dt=_F32), e(M, dt=_F32)
             ops.layernorm_fwd(x1, w["g1"], w["b1"], h1, mean1, rstd1, LN_EPS)
-            u, g = e(M, 4 * d), e(M, 4 * d)
-            ops.linear(h1, w["w1"], w["bb1"], u, epi=L.M3P_EPI_GELU, out2=g)
+            gp, g = e(M, 4 * d), e(M, 4 * d)  # gelu'(u) (stash for the backward) and gelu(u)
+            ops.linear(h1, w["w1"], w["bb1"], gp, epi=L.M3P_EPI_GELU, out2=g)
             x2 = e(M, d)
             ops.linear(g, w["w2"], w["bb2"], x2, epi=L.M3P_EPI_DROP_RES, aux=h1, drop_p=p_drop, seed=s2)
             hn, mean2, rstd2 = e(M, d), e(M, dt=_F32), e(M, dt=_F32)
             ops.layernorm_fwd(x2, w["g2"], w["b2"], hn, mean2, rstd2, LN_EPS, seqlen=seqlen, S=S)
             if need_grad:
-                st["layers"].append(dict(h=h, qkv=qkv, ctx=ctx, lse=lse, x1=x1, h1=h1, mean1=mean1, rstd1=rstd1, u=u,
+                st["layers"].append(dict(h=h, qkv=qkv, ctx=ctx, lse=lse, x1=x1, h1=h1, mean1=mean1, rstd1=rstd1, gp=gp,
                                          g=g, x2=x2, mean2=mean2, rstd2=rstd2, s1=s1, s2=s2, sa=sa))
             h = hn
         return h, st
@@ -608,7 +608,7 @@ class TransformerModel(nn.Module):
                 dx2d = dx2
             # lin2 dgrad fused with gelu'(u); lin2 wgrad                (:224-225)
             du = e(M, 4 * d)
-            ops.dgrad(dx2d, w["w2"], du, epi=L.M3P_EPI_DGELU, aux=s["u"])
+            ops.dgrad(dx2d, w["w2"], du, epi=L.M3P_EPI_DGELU, aux=s["gp"])
             ops.wgrad(dx2d, s["g"], gr["w2"])
             # lin1 dgrad + residual branch; lin1 wgrad / bias           (:223, :956)
             dh1 = e(M, d)
@@ -817,8 +817,8 @@ class _ObjFn(torch.autograd.Function):
         idx = torch.arange(n, device=dev, dtype=torch.int64)
         rows = torch.empty(n, d, dtype=_BF16, device=dev)
         ops.gather_rows(t, idx, R, t.stride(0), t.stride(1), rows, n, d)
-        u, g = torch.empty(n, d, dtype=_BF16, device=dev), torch.empty(n, d, dtype=_BF16, device=dev)
-        ops.linear(rows, model._w16("transformer_obj.dense.weight"), model._w32("transformer_obj.dense.bias"), u,
+        gp, g = torch.empty(n, d, dtype=_BF16, device=dev), torch.empty(n, d, dtype=_BF16, device=dev)
+        ops.linear(rows, model._w16("transformer_obj.dense.weight"), model._w32("transformer_obj.dense.bias"), gp,
                    epi=L.M3P_EPI_GELU, out2=g)
         tn, mean, rstd = torch.empty(n, d, dtype=_BF16, device=dev), torch.empty(n, dtype=_F32, device=dev), \
             torch.empty(n, dtype=_F32, device=dev)
@@ -831,7 +831,7 @@ class _ObjFn(torch.autograd.Function):
             torch.empty((), dtype=_F32, device=dev)
         ops.cross_entropy_fwd(logits, yv, N_OBJ, -1, loss, lse, inv)
         ctx.model, ctx.shape = model, (B, R, d)
-        ctx.save_for_backward(rows, u, g, tn, mean, rstd, logits, yv, lse, inv)
+        ctx.save_for_backward(rows, gp, g, tn, mean, rstd, logits, yv, lse, inv)
         scores = logits.float() if get_scores else logits
         ctx.mark_non_differentiable(scores)
         return scores, loss
@@ -839,7 +839,7 @@ class _ObjFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, _dscores, dloss):
         model = ctx.model
-        rows, u, g, tn, mean, rstd, logits, yv, lse, inv = ctx.saved_tensors
+        rows, gp, g, tn, mean, rstd, logits, yv, lse, inv = ctx.saved_tensors
         B, R, d = ctx.shape
         n, dev = B * R, rows.device
         model.attach_grads()
@@ -855,7 +855,7 @@ class _ObjFn(torch.autograd.Function):
                           dgamma=model._g("transformer_obj.LayerNorm.weight"),
                           dbeta=model._g("transformer_obj.LayerNorm.bias"))
         du = torch.empty(n, d, dtype=_BF16, device=dev)
-        ops.gelu_bwd(dg, u, du)
+        ops.gelu_bwd(dg, gp, du)
         ops.wgrad(du, rows, model._g("transformer_obj.dense.weight"))
         ops.colsum(du, model._g("transformer_obj.dense.bias"))
         dt = None

@@ -58,7 +58,7 @@ def _model(T, ns, sd=None):
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
 def test_gemm_operand_layouts(m3p, a_mn, b_mn):
     from m3p_b200 import ops
-    m, n, k = 300, 392, 200
+    m, n, k = 304, 392, 200  # MN-major operands need pitches that are multiples of 8 (TMA 16-byte rule)
     g = torch.Generator(device="cuda").manual_seed(1)
     A = (torch.randn(m, k, device="cuda", generator=g) * 0.5).bfloat16()
     B = (torch.randn(n, k, device="cuda", generator=g) * 0.5).bfloat16()
@@ -110,7 +110,9 @@ def test_attention_forward_backward(m3p, B, S, H, ragged):
     dqkv = torch.zeros(B * S, 3 * d, device="cuda", dtype=torch.bfloat16)
     ops.attention_bwd(qkv, seqlen, B, S, H, 0.125, 0.0, 0, ctx, lse, dctx, dqkv)
     for i, name in enumerate(("dq", "dk", "dv")):
-        assert _rel(dqkv[:, i * d:(i + 1) * d], q32.grad[:, i * d:(i + 1) * d]) < KERNEL_TOL, name
+        got, want = dqkv[:, i * d:(i + 1) * d].float(), q32.grad[:, i * d:(i + 1) * d]
+        # absolute floor: with a single key the softmax is constant and dq, dk are exactly 0
+        assert float((got - want).norm()) < KERNEL_TOL * max(float(want.norm()), 1e-2), name
 
 
 def test_attention_dropout_is_deterministic_and_consistent(m3p):
@@ -388,3 +390,34 @@ def test_full_size_data_parallel_linearity(m3p):
         grads.append((model._flat_grad.clone(), model._emb_grad.clone()))
     for j in range(2):
         assert _rel(grads[0][j], 0.5 * (grads[1][j] + grads[2][j])) < 2e-2
+
+
+def test_gemm_fused_epilogues(m3p):
+    """bias / erf-GELU (+ stashed derivative) / dropout+residual / stashed-derivative multiply / tanh."""
+    from m3p_b200 import lib as L, ops
+    m, n, k = 300, 392, 200
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = (torch.randn(m, k, device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn(n, k, device="cuda", generator=g) * 0.5).bfloat16()
+    bias = torch.randn(n, device="cuda", generator=g)
+    aux = torch.randn(m, n, device="cuda", generator=g).bfloat16()
+    ref = A.float() @ B.float().t() + bias
+    o, o2 = torch.empty(m, n, device="cuda", dtype=torch.bfloat16), torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, m, n, k, o, bias=bias, epi=L.M3P_EPI_GELU, out2=o2)
+    cdf = 0.5 * (1 + torch.erf(ref / 2 ** 0.5))
+    assert _rel(o2, ref * cdf) < KERNEL_TOL                                                    # transformer.py:56
+    assert _rel(o, cdf + ref * torch.exp(-0.5 * ref * ref) / (2 * 3.141592653589793) ** 0.5) < KERNEL_TOL
+    ops.gemm(A, B, m, n, k, o, bias=bias, epi=L.M3P_EPI_DROP_RES, aux=aux)
+    assert _rel(o, ref + aux.float()) < KERNEL_TOL
+    ops.gemm(A, B, m, n, k, o, bias=bias, epi=L.M3P_EPI_DROP_RES, aux=aux, drop_p=0.1, seed=77)
+    ops.gemm(A, B, m, n, k, o2, bias=bias, epi=L.M3P_EPI_DROP_RES, aux=aux, drop_p=0.1, seed=77)
+    assert bool((o == o2).all())
+    dlt = o.float() - aux.float()
+    kept = (dlt.abs() > 1e-6).float().mean().item()
+    assert abs(kept - 0.9) < 0.01
+    ok = ((dlt - ref / 0.9).abs() < 0.02 * ref.abs() / 0.9 + 0.06) | (dlt.abs() < 1e-6)
+    assert ok.float().mean().item() > 0.999
+    ops.gemm(A, B, m, n, k, o, epi=L.M3P_EPI_DGELU, aux=aux)
+    assert _rel(o, (ref - bias) * aux.float()) < KERNEL_TOL
+    ops.gemm(A, B, m, n, k, o, bias=bias, epi=L.M3P_EPI_TANH, alpha=0.1)
+    assert _rel(o, torch.tanh(0.1 * (ref - bias) + bias)) < KERNEL_TOL

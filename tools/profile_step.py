@@ -19,8 +19,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--heads", default="itm")
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--steps", type=int, default=1)
+ap.add_argument("--layers", type=int, default=0, help="override the layer count (ncu --set full captures)")
 a = ap.parse_args()
-cfg = bench.CFG
+cfg = dict(bench.CFG)
+if a.layers:
+    cfg["n_layers"] = a.layers
 torch.manual_seed(0)
 model = TransformerModel(bench.namespace(cfg), is_encoder=True, with_output=True, is_crossModal=True).cuda().train()
 batch = synthetic_batch(a.batch, cfg["T"], cfg["R"], cfg["n_words"], sample_n=cfg["sample_n"], seed=1234, device="cuda")
