@@ -130,43 +130,66 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
 
   // ---- softmax: one thread per query row ----
+  // Interior 32-key chunks (entirely below the key length L) take a path without per-element masking;
+  // only the chunk that straddles L pays for the compares.  The dropout scale 1/(1-p) is folded into
+  // the final 1/sum normalisation, so a dropped weight is a plain select-to-zero.
   const int row = warp * 32 + lane;
   const int q_idx = mt * 128 + row;
   int L = p.seqlen[b];
   L = L < 0 ? 0 : (L > p.S ? p.S : L);
   const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   const int nchunk = (p.n_kv + 31) >> 5;
+  const int nfull = L >> 5;  // chunks with every key valid
   float mx = -INFINITY;
   for (int c = 0; c < nchunk; ++c) {
+    if (c * 32 >= L) break;
     uint32_t acc[32];
     tmem_ld_32x32b_x32(t_row + c * 32, acc);
     tmem_ld_wait();
+    if (c < nfull) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c * 32 + j < L) mx = fmaxf(mx, __uint_as_float(acc[j]));
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(acc[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c * 32 + j < L) mx = fmaxf(mx, __uint_as_float(acc[j]));
+    }
   }
   const float mxs = (L > 0) ? mx * p.scale_log2 : 0.f;
   float sum = 0.f;
   const int bh = b * p.H + h;
   for (int c = 0; c < nchunk; ++c) {
-    uint32_t acc[32];
-    tmem_ld_32x32b_x32(t_row + c * 32, acc);
-    tmem_ld_wait();
     float pv[32];
+    if (c * 32 < L) {
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(t_row + c * 32, acc);
+      tmem_ld_wait();
+      if (c < nfull) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float e = ex2(fmaf(__uint_as_float(acc[j]), p.scale_log2, -mxs));
-      pv[j] = (c * 32 + j < L) ? e : 0.f;
-      sum += pv[j];
-    }
-    if (p.thr16 != 0) {
-      const uint32_t e0 = attn_drop_base(bh, q_idx, c * 32);
+        for (int j = 0; j < 32; ++j) {
+          pv[j] = ex2(fmaf(__uint_as_float(acc[j]), p.scale_log2, -mxs));
+          sum += pv[j];
+        }
+      } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const uint32_t hsh = drop_hash((e0 >> 1) + j, p.seed_lo, p.seed_hi);
-        pv[2 * j] = ((hsh & 0xffffu) >= p.thr16) ? pv[2 * j] * p.drop_scale : 0.f;
-        pv[2 * j + 1] = ((hsh >> 16) >= p.thr16) ? pv[2 * j + 1] * p.drop_scale : 0.f;
+        for (int j = 0; j < 32; ++j) {
+          const float e = ex2(fmaf(__uint_as_float(acc[j]), p.scale_log2, -mxs));
+          pv[j] = (c * 32 + j < L) ? e : 0.f;
+          sum += pv[j];
+        }
       }
+      if (p.thr16 != 0) {
+        const uint32_t e0 = attn_drop_base(bh, q_idx, c * 32);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t hsh = drop_hash((e0 >> 1) + j, p.seed_lo, p.seed_hi);
+          pv[2 * j] = ((hsh & 0xffffu) >= p.thr16) ? pv[2 * j] : 0.f;
+          pv[2 * j + 1] = ((hsh >> 16) >= p.thr16) ? pv[2 * j + 1] : 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pv[j] = 0.f;
     }
     // keys [c*32, c*32+32) live in k-block c/2, 16-byte chunks (c&1)*4 .. +3 of this row
     uint8_t* blk = sP + (c >> 1) * TILE16K;
@@ -200,7 +223,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
 
   {
-    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+    const float inv = sum > 0.f ? p.drop_scale / sum : 0.f;  // dropout's 1/(1-p) folded in here
     uint32_t o0[32], o1[32];
     tmem_ld_32x32b_x32(t_row, o0);
     tmem_ld_32x32b_x32(t_row + 32, o1);
@@ -299,7 +322,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   // ---- delta = rowsum(dO * O), lse: one thread per query row (global reads overlap the TMA) ----
   {
     const int r = threadIdx.x;
-    float dl = 0.f, ls = 0.f;
+    float dl = 0.f, ls = INFINITY;  // phantom query rows: exp2(s - inf) = 0, no per-element test needed
     if (r < p.S) {
       const long long off = (static_cast<long long>(b) * p.S + r) * p.d + h * ATT_DH;
       const uint4* a4 = reinterpret_cast<const uint4*>(p.dctx + off);
@@ -331,110 +354,144 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint32_t ph_sd = 0, ph_g = 0;
   int g_pending = 0;
 
-  for (int j = 0; j < NT; ++j) {
-    for (int i = 0; i < NT; ++i) {
-      if (threadIdx.x == 0) {
-        if (i == 0 && j == 0) mbar_wait(bar_ld, 0);
-        tc_fence_after();
-        const uint32_t qa = smem_u32(sQ) + i * TILE16K, ka = smem_u32(sK) + j * TILE16K;
-        const uint32_t da = smem_u32(sdO) + i * TILE16K, va = smem_u32(sV) + j * TILE16K;
+  // S = Q_i K_j^T and dP = dO_i V_j^T for block (i, j) into TMEM; one thread issues.
+  auto issue_s_dp = [&](int i, int j) {
+    tc_fence_after();
+    const uint32_t qa = smem_u32(sQ) + i * TILE16K, ka = smem_u32(sK) + j * TILE16K;
+    const uint32_t da = smem_u32(sdO) + i * TILE16K, va = smem_u32(sV) + j * TILE16K;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem_base + TM_S, make_smem_desc(qa + k * 32, 0, 1024), make_smem_desc(ka + k * 32, 0, 1024),
-                  idesc_s, k > 0 ? 1u : 0u);
+    for (int k = 0; k < 4; ++k)
+      umma_ss(tmem_base + TM_S, make_smem_desc(qa + k * 32, 0, 1024), make_smem_desc(ka + k * 32, 0, 1024), idesc_s,
+              k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem_base + TM_DP, make_smem_desc(da + k * 32, 0, 1024), make_smem_desc(va + k * 32, 0, 1024),
-                  idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_sd);
-      }
-      __syncwarp();
-      mbar_wait(bar_sd, ph_sd);
-      ph_sd ^= 1;
-      // the previous block's dV/dK/dQ MMAs still read sP / sdS: wait before overwriting them
-      if (g_pending) {
-        mbar_wait(bar_g, ph_g);
-        ph_g ^= 1;
-        g_pending = 0;
-      }
-      __syncwarp();
-      tc_fence_after();
+    for (int k = 0; k < 4; ++k)
+      umma_ss(tmem_base + TM_DP, make_smem_desc(da + k * 32, 0, 1024), make_smem_desc(va + k * 32, 0, 1024), idesc_s,
+              k > 0 ? 1u : 0u);
+    umma_commit(bar_sd);
+  };
 
-      const int q = i * 128 + row;
-      const bool q_ok = q < p.S;
-      const float lse2 = s_lse[q], delta = s_delta[q];
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        const int col0 = half * 64 + c * 32;  // column inside the 128-key tile
-        uint32_t sacc[32], dacc[32];
-        tmem_ld_32x32b_x32(t_lane + TM_S + col0, sacc);
-        tmem_ld_32x32b_x32(t_lane + TM_DP + col0, dacc);
-        tmem_ld_wait();
-        const int key0 = j * 128 + col0;
-        float pd[32], ds[32];
-        uint32_t e0 = 0;
-        if (p.thr16 != 0) e0 = attn_drop_base(bh, q, key0);
+  if (threadIdx.x == 0) {
+    mbar_wait(bar_ld, 0);
+    issue_s_dp(0, 0);
+  }
+  const int nblocks = NT * NT;
+  for (int n = 0; n < nblocks; ++n) {
+    const int j = n / NT, i = n % NT;
+    __syncwarp();
+    mbar_wait(bar_sd, ph_sd);
+    ph_sd ^= 1;
+    __syncwarp();
+    tc_fence_after();
+
+    // ---- P and dS for this thread's row x 64 keys, kept packed in registers ----
+    const int q = i * 128 + row;
+    const float lse2 = s_lse[q], delta = s_delta[q];
+    uint32_t ppk[2][16], dpk[2][16];
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const bool ok = q_ok && (key0 + jj < L);
-          const float pr = ok ? ex2(fmaf(__uint_as_float(sacc[jj]), p.scale_log2, -lse2)) : 0.f;
-          float ks = 1.0f;
-          if (p.thr16 != 0) {
-            const uint32_t hsh = drop_hash((e0 >> 1) + (jj >> 1), p.seed_lo, p.seed_hi);
-            const uint32_t hv = (jj & 1) ? (hsh >> 16) : (hsh & 0xffffu);
-            ks = (hv >= p.thr16) ? p.drop_scale : 0.f;
+    for (int c = 0; c < 2; ++c) {
+      const int col0 = half * 64 + c * 32;  // column inside the 128-key tile
+      const int key0 = j * 128 + col0;
+      uint32_t sacc[32], dacc[32];
+      tmem_ld_32x32b_x32(t_lane + TM_S + col0, sacc);
+      tmem_ld_32x32b_x32(t_lane + TM_DP + col0, dacc);
+      tmem_ld_wait();
+      float pd[32], ds[32];
+      if (key0 >= L) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) { pd[jj] = 0.f; ds[jj] = 0.f; }
+      } else {
+        const bool interior = key0 + 32 <= L;
+        if (p.thr16 != 0) {
+          const uint32_t e0 = attn_drop_base(bh, q, key0);
+#pragma unroll
+          for (int jp = 0; jp < 16; ++jp) {
+            const uint32_t hsh = drop_hash((e0 >> 1) + jp, p.seed_lo, p.seed_hi);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int jj = 2 * jp + t;
+              const uint32_t hv = t ? (hsh >> 16) : (hsh & 0xffffu);
+              const float ks = (hv >= p.thr16) ? p.drop_scale : 0.f;
+              float pr = ex2(fmaf(__uint_as_float(sacc[jj]), p.scale_log2, -lse2));
+              if (!interior) pr = (key0 + jj < L) ? pr : 0.f;
+              pd[jj] = pr * ks;
+              ds[jj] = pr * fmaf(__uint_as_float(dacc[jj]), ks, -delta);
+            }
           }
-          pd[jj] = pr * ks;
-          ds[jj] = ok ? pr * (__uint_as_float(dacc[jj]) * ks - delta) * p.scale : 0.f;
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            float pr = ex2(fmaf(__uint_as_float(sacc[jj]), p.scale_log2, -lse2));
+            if (!interior) pr = (key0 + jj < L) ? pr : 0.f;
+            pd[jj] = pr;
+            ds[jj] = pr * (__uint_as_float(dacc[jj]) - delta);
+          }
         }
-        uint8_t* pblk = sP + half * TILE16K;
-        uint8_t* dblk = sdS + half * TILE16K;
+      }
+#pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        ppk[c][g] = pack_bf16x2(pd[2 * g], pd[2 * g + 1]);
+        dpk[c][g] = pack_bf16x2(ds[2 * g], ds[2 * g + 1]);
+      }
+    }
+    // S / dP are in registers: TMEM is free for the next block's score MMAs, which then run on the
+    // tensor pipe while this block's P / dS are written out and its dV / dK / dQ MMAs are queued.
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0 && n + 1 < nblocks) issue_s_dp((n + 1) % NT, (n + 1) / NT);
+    // the previous block's dV/dK/dQ MMAs still read sP / sdS: wait before overwriting them
+    if (g_pending) {
+      __syncwarp();
+      mbar_wait(bar_g, ph_g);
+      ph_g ^= 1;
+      g_pending = 0;
+      __syncwarp();
+    }
+    {
+      uint8_t* pblk = sP + half * TILE16K;
+      uint8_t* dblk = sdS + half * TILE16K;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint32_t off = swz_off(row, c * 4 + g);
-          *reinterpret_cast<uint4*>(pblk + off) =
-              make_uint4(pack_bf16x2(pd[8 * g + 0], pd[8 * g + 1]), pack_bf16x2(pd[8 * g + 2], pd[8 * g + 3]),
-                         pack_bf16x2(pd[8 * g + 4], pd[8 * g + 5]), pack_bf16x2(pd[8 * g + 6], pd[8 * g + 7]));
-          *reinterpret_cast<uint4*>(dblk + off) =
-              make_uint4(pack_bf16x2(ds[8 * g + 0], ds[8 * g + 1]), pack_bf16x2(ds[8 * g + 2], ds[8 * g + 3]),
-                         pack_bf16x2(ds[8 * g + 4], ds[8 * g + 5]), pack_bf16x2(ds[8 * g + 6], ds[8 * g + 7]));
+          *reinterpret_cast<uint4*>(pblk + off) = make_uint4(ppk[c][4 * g], ppk[c][4 * g + 1], ppk[c][4 * g + 2], ppk[c][4 * g + 3]);
+          *reinterpret_cast<uint4*>(dblk + off) = make_uint4(dpk[c][4 * g], dpk[c][4 * g + 1], dpk[c][4 * g + 2], dpk[c][4 * g + 3]);
         }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncthreads();
-
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS);
-        const uint32_t doa = smem_u32(sdO) + i * TILE16K, qa = smem_u32(sQ) + i * TILE16K;
-        const uint32_t ka = smem_u32(sK) + j * TILE16K;
-        // dV_j += Pd^T dO_i ; dK_j += dS^T Q_i      (M = 128 keys, N = 64, K = 128 queries)
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss(tmem_base + TM_DV, make_smem_desc(pa + k * 2048, TILE16K, 1024),
-                  make_smem_desc(doa + k * 2048, TILE16K, 1024), idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss(tmem_base + TM_DK, make_smem_desc(sa + k * 2048, TILE16K, 1024),
-                  make_smem_desc(qa + k * 2048, TILE16K, 1024), idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-        // dQ_i += dS K_j                             (M = 128 queries, N = 64, K = 128 keys)
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss(tmem_base + TM_DQ + i * ATT_DH, make_smem_desc(sa + (k >> 2) * TILE16K + (k & 3) * 32, 0, 1024),
-                  make_smem_desc(ka + k * 2048, TILE16K, 1024), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(bar_g);
-      }
-      g_pending = 1;
     }
-    // ---- dK_j, dV_j complete: TMEM -> bf16 -> dqkv ----
-    __syncwarp();
-    mbar_wait(bar_g, ph_g);
-    ph_g ^= 1;
-    g_pending = 0;
-    __syncwarp();
-    tc_fence_after();
-    {
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS);
+      const uint32_t doa = smem_u32(sdO) + i * TILE16K, qa = smem_u32(sQ) + i * TILE16K;
+      const uint32_t ka = smem_u32(sK) + j * TILE16K;
+      // dV_j += Pd^T dO_i ; dK_j += dS^T Q_i      (M = 128 keys, N = 64, K = 128 queries)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_ss(tmem_base + TM_DV, make_smem_desc(pa + k * 2048, TILE16K, 1024),
+                make_smem_desc(doa + k * 2048, TILE16K, 1024), idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_ss(tmem_base + TM_DK, make_smem_desc(sa + k * 2048, TILE16K, 1024),
+                make_smem_desc(qa + k * 2048, TILE16K, 1024), idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+      // dQ_i += dS K_j                             (M = 128 queries, N = 64, K = 128 keys)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_ss(tmem_base + TM_DQ + i * ATT_DH, make_smem_desc(sa + (k >> 2) * TILE16K + (k & 3) * 32, 0, 1024),
+                make_smem_desc(ka + k * 2048, TILE16K, 1024), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
+      umma_commit(bar_g);
+    }
+    g_pending = 1;
+
+    if (i == NT - 1) {
+      // ---- dK_j, dV_j complete: TMEM -> bf16 -> dqkv (the softmax scale is applied here, not per element) ----
+      __syncwarp();
+      mbar_wait(bar_g, ph_g);
+      ph_g ^= 1;
+      g_pending = 0;
+      __syncwarp();
+      tc_fence_after();
       uint32_t a[32], v[32];
       tmem_ld_32x32b_x32(t_lane + TM_DK + half * 32, a);
       tmem_ld_32x32b_x32(t_lane + TM_DV + half * 32, v);
@@ -442,13 +499,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       const int key = j * 128 + row;
       if (key < p.S) {
         __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.S + key) * (3 * p.d) + h * ATT_DH + half * 32;
-        store_acc32(base + p.d, a, 1.0f);
+        store_acc32(base + p.d, a, p.scale);
         store_acc32(base + 2 * p.d, v, 1.0f);
       }
+      tc_fence_before();  // ordered before the next block's barriers, which precede the MMAs that reuse dK / dV
     }
-    tc_fence_before();
-    __syncthreads();
   }
+  __syncthreads();
   // ---- dQ ----
   tc_fence_after();
   for (int i = 0; i < NT; ++i) {
@@ -458,7 +515,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const int q = i * 128 + row;
     if (q < p.S) {
       __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.S + q) * (3 * p.d) + h * ATT_DH + half * 32;
-      store_acc32(base, a, 1.0f);
+      store_acc32(base, a, p.scale);
     }
   }
   tc_fence_before();

@@ -99,6 +99,24 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * e, 0.3989422804014327f, 0.5f * (1.0f + er));
 }
 
+// GELU and its derivative from ONE erf / exp evaluation, on raw MUFU approximations (no denormal /
+// range fix-up code: the arguments are bounded, |erf err| stays ~1e-6, far below bf16 rounding).
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& gp) {
+  const float a = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, a, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));  // exp(-x^2 / 2)
+  const float er = copysignf(fmaf(-poly, e, 1.0f), x);
+  const float cdf = fmaf(0.5f, er, 0.5f);
+  g = x * cdf;
+  gp = fmaf(x * e, 0.3989422804014327f, cdf);
+}
+
 // ---- warp reductions ----------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -155,10 +155,11 @@ struct LnBwdParams {
   long long rows; int d;
 };
 
+// Pass 1 — one warp per row, no per-thread column accumulators (keeps registers low and occupancy high:
+// the kernel is latency-bound on its two row loads).
 template <typename XT, typename DYT, typename DXT, int MAXC>
-__global__ void __launch_bounds__(EW_THREADS)
-ln_bwd_kernel(const LnBwdParams p) {
-  extern __shared__ float sacc[];  // [EW_WARPS][MAXC * 8 * 32]
+__global__ void __launch_bounds__(EW_THREADS, (MAXC <= 3) ? 3 : 2)
+ln_bwd_dx_kernel(const LnBwdParams p) {
   const int d = p.d;
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
@@ -167,13 +168,6 @@ ln_bwd_kernel(const LnBwdParams p) {
   const XT* x = reinterpret_cast<const XT*>(p.x);
   const DYT* dy = reinterpret_cast<const DYT*>(p.dy);
   DXT* dx = reinterpret_cast<DXT*>(p.dx);
-
-  float acc_g[MAXC][8], acc_b[MAXC][8], acc_bias[MAXC][8];
-#pragma unroll
-  for (int c = 0; c < MAXC; ++c)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { acc_g[c][j] = 0.f; acc_b[c][j] = 0.f; acc_bias[c][j] = 0.f; }
-
   for (long long row = warp0; row < p.rows; row += nwarps) {
     bool valid = true;
     if (p.seqlen != nullptr) valid = (row % p.S) < p.seqlen[row / p.S];
@@ -192,13 +186,10 @@ ln_bwd_kernel(const LnBwdParams p) {
           drop8((uint32_t)row * (uint32_t)d + ch * 8, p.dy_seed_lo, p.dy_seed_hi, p.dy_thr16, p.dy_scale, dv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float dyv = valid ? dv[j] : 0.f;
           xh[c][j] = (xv[j] - mean) * rstd;
-          g[c][j] = dyv * gm[j];
+          g[c][j] = valid ? dv[j] * gm[j] : 0.f;
           s1 += g[c][j];
-          s2 += g[c][j] * xh[c][j];
-          acc_g[c][j] += dyv * xh[c][j];
-          acc_b[c][j] += dyv;
+          s2 = fmaf(g[c][j], xh[c][j], s2);
         }
       }
     }
@@ -217,60 +208,104 @@ ln_bwd_kernel(const LnBwdParams p) {
             drop8((uint32_t)row * (uint32_t)d + ch * 8, p.dx_seed_lo, p.dx_seed_hi, p.dx_thr16, p.dx_scale, o);
           store8(p.dx_drop + row * d + ch * 8, o);
         }
-        if (p.dbias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            // bias gradient sees the bf16-rounded value the GEMMs will consume
-            acc_bias[c][j] += o[j];
-          }
-        }
       }
     }
   }
-  // cross-warp reduction: every warp owns the same (lane -> columns) map, so partials are laid out
-  // [warp][slot][lane] (conflict-free), summed over warps, then one global atomic per column per CTA
-  const int warp = threadIdx.x >> 5;
-  constexpr int SLOTS = MAXC * 8 * 32;
-  auto reduce_one = [&](float (&acc)[MAXC][8], const float* wanted, int which) {
-    if (wanted == nullptr) return;  // uniform across the CTA
-    float* dst = p.partial + ((long long)blockIdx.x * 3 + which) * d;
+}
+
+// Pass 2 — column sums over rows: dgamma = sum dy_eff * xhat, dbeta = sum dy_eff, dbias = sum dx_drop.
+// A thread owns 8 columns and walks a row range 4 rows at a time (12 vector loads in flight); dy / x
+// were just read by pass 1 and dx_drop just written, so this pass mostly hits L2.  Per-CTA partials go
+// to scratch and are folded by reduce_partials.
+template <typename XT, typename DYT, typename BT>
+__global__ void __launch_bounds__(128)
+ln_bwd_cols_kernel(const LnBwdParams p, const BT* __restrict__ bias_src, long long rows_per_cta) {
+  const int d = p.d;
+  const int col0 = threadIdx.x * 8;
+  if (col0 >= d) return;
+  const XT* x = reinterpret_cast<const XT*>(p.x);
+  const DYT* dy = reinterpret_cast<const DYT*>(p.dy);
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < p.rows ? r0 + rows_per_cta : p.rows;
+  float ag[8], ab[8], abias[8];
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c)
+  for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; abias[j] = 0.f; }
+  const bool want_gb = (p.dgamma != nullptr) || (p.dbeta != nullptr);
+  for (long long r = r0; r < r1; r += 4) {
+    float xv[4][8], dv[4][8], bv[4][8], mean[4], rstd[4];
+    bool ok[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sacc[warp * SLOTS + (c * 8 + j) * 32 + lane] = acc[c][j];
-    __syncthreads();
-    for (int slot = threadIdx.x; slot < SLOTS; slot += EW_THREADS) {
-      float sum = 0.f;
-#pragma unroll
-      for (int w = 0; w < EW_WARPS; ++w) sum += sacc[w * SLOTS + slot];
-      const int k = slot >> 5, l = slot & 31;
-      const int ch = l + 32 * (k >> 3);
-      if (ch < nchunks) dst[ch * 8 + (k & 7)] = sum;
+    for (int i = 0; i < 4; ++i) {
+      const long long row = r + i;
+      ok[i] = row < r1;
+      const long long rr = ok[i] ? row : r0;
+      if (want_gb) {
+        load8(x + rr * d + col0, xv[i]);
+        load8(dy + rr * d + col0, dv[i]);
+        mean[i] = p.mean[rr];
+        rstd[i] = p.rstd[rr];
+      }
+      if (bias_src != nullptr) load8(bias_src + rr * d + col0, bv[i]);
     }
-    __syncthreads();
-  };
-  reduce_one(acc_g, p.dgamma, 0);
-  reduce_one(acc_b, p.dbeta, 1);
-  reduce_one(acc_bias, p.dbias, 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long row = r + i;
+      if (!ok[i]) continue;
+      if (want_gb) {
+        bool valid = true;
+        if (p.seqlen != nullptr) valid = (row % p.S) < p.seqlen[row / p.S];
+        if (valid) {
+          if (p.dy_thr16 != 0)
+            drop8((uint32_t)row * (uint32_t)d + col0, p.dy_seed_lo, p.dy_seed_hi, p.dy_thr16, p.dy_scale, dv[i]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ag[j] = fmaf(dv[i][j], (xv[i][j] - mean[i]) * rstd[i], ag[j]);
+            ab[j] += dv[i][j];
+          }
+        }
+      }
+      if (bias_src != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) abias[j] += bv[i][j];
+      }
+    }
+  }
+  float* dst = p.partial + (long long)blockIdx.x * 3 * d + col0;
+  *reinterpret_cast<float4*>(dst) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(ag[4], ag[5], ag[6], ag[7]);
+  *reinterpret_cast<float4*>(dst + d) = make_float4(ab[0], ab[1], ab[2], ab[3]);
+  *reinterpret_cast<float4*>(dst + d + 4) = make_float4(ab[4], ab[5], ab[6], ab[7]);
+  *reinterpret_cast<float4*>(dst + 2 * d) = make_float4(abias[0], abias[1], abias[2], abias[3]);
+  *reinterpret_cast<float4*>(dst + 2 * d + 4) = make_float4(abias[4], abias[5], abias[6], abias[7]);
 }
 
 template <typename XT, typename DYT, typename DXT>
 static int launch_ln_bwd(LnBwdParams p, cudaStream_t stream) {
-  // one CTA per SM (the kernel is register-heavy: 1 CTA / SM), every warp streams rows; the per-CTA
-  // column sums go to scratch and are folded by reduce_partials (no same-address atomics storm)
-  long long need = (p.rows + EW_WARPS - 1) / EW_WARPS;
-  const long long cap = (long long)sm_count() * 2;
-  const int grid = (int)(need < cap ? need : cap);
-  p.partial = scratch_f32((size_t)grid * 3 * p.d);
+  const int grid = ew_grid(p.rows);
+  if (p.d <= 256) ln_bwd_dx_kernel<XT, DYT, DXT, 1><<<grid, EW_THREADS, 0, stream>>>(p);
+  else if (p.d <= 768) ln_bwd_dx_kernel<XT, DYT, DXT, 3><<<grid, EW_THREADS, 0, stream>>>(p);
+  else ln_bwd_dx_kernel<XT, DYT, DXT, 4><<<grid, EW_THREADS, 0, stream>>>(p);
+  M3P_CUDA_OK(cudaGetLastError());
+  if (!(p.dgamma || p.dbeta || p.dbias)) return M3P_OK;
+  // column sums: ~4 CTAs per SM, each a contiguous row range (multiple of 4 rows)
+  long long parts = (long long)sm_count() * 4;
+  long long rpc = (p.rows + parts - 1) / parts;
+  rpc = (rpc + 3) / 4 * 4;
+  if (rpc < 8) rpc = 8;
+  parts = (p.rows + rpc - 1) / rpc;
+  p.partial = scratch_f32((size_t)parts * 3 * p.d);
   if (p.partial == nullptr) return M3P_ERR_CUDA;
-  auto smem = [](int maxc) { return (size_t)EW_WARPS * maxc * 8 * 32 * sizeof(float); };
-  if (p.d <= 256) ln_bwd_kernel<XT, DYT, DXT, 1><<<grid, EW_THREADS, smem(1), stream>>>(p);
-  else if (p.d <= 768) ln_bwd_kernel<XT, DYT, DXT, 3><<<grid, EW_THREADS, smem(3), stream>>>(p);
-  else ln_bwd_kernel<XT, DYT, DXT, 4><<<grid, EW_THREADS, smem(4), stream>>>(p);
+  const int threads = ((p.d / 8 + 31) / 32) * 32;  // d <= 1024 -> <= 128 threads
+  if (p.dbias == nullptr) {
+    ln_bwd_cols_kernel<XT, DYT, DXT><<<(int)parts, threads, 0, stream>>>(p, static_cast<const DXT*>(nullptr), rpc);
+  } else if (p.dx_drop != nullptr) {
+    ln_bwd_cols_kernel<XT, DYT, __nv_bfloat16><<<(int)parts, threads, 0, stream>>>(p, p.dx_drop, rpc);
+  } else {
+    ln_bwd_cols_kernel<XT, DYT, DXT><<<(int)parts, threads, 0, stream>>>(p, reinterpret_cast<const DXT*>(p.dx), rpc);
+  }
   M3P_CUDA_OK(cudaGetLastError());
   float* outs[3] = {p.dgamma, p.dbeta, p.dbias};
-  if (p.dgamma || p.dbeta || p.dbias) return reduce_partials(p.partial, grid, p.d, outs, 3, stream);
-  return M3P_OK;
+  return reduce_partials(p.partial, (int)parts, p.d, outs, 3, stream);
 }
 
 // =================================================================================================

@@ -15,6 +15,8 @@
 // Operand layouts: either operand may be K-major (reduction dim contiguous: forward "TN" GEMMs)
 // or MN-major (output dim contiguous: dgrad uses an MN-major B, wgrad MN-major A and B), so no
 // transposed copies of weights or activations are ever made.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -60,15 +62,13 @@ __device__ __forceinline__ void decode_unit(const GemmKernelParams& p, int u, in
 // 16 columns = 32 bytes of bf16 per row: every global access of a thread is one full 32-byte sector.
 constexpr int EW = 16;  // epilogue chunk width (columns)
 
-__device__ __forceinline__ void load_bf16x16(const __nv_bfloat16* p, float* x) {
-  const uint4* a4 = reinterpret_cast<const uint4*>(p);
+__device__ __forceinline__ void unpack_bf16x16(const uint4* t, float* x) {
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    const uint4 t = __ldg(a4 + j);
-    x[8 * j + 0] = bf16_lo(t.x); x[8 * j + 1] = bf16_hi(t.x);
-    x[8 * j + 2] = bf16_lo(t.y); x[8 * j + 3] = bf16_hi(t.y);
-    x[8 * j + 4] = bf16_lo(t.z); x[8 * j + 5] = bf16_hi(t.z);
-    x[8 * j + 6] = bf16_lo(t.w); x[8 * j + 7] = bf16_hi(t.w);
+    x[8 * j + 0] = bf16_lo(t[j].x); x[8 * j + 1] = bf16_hi(t[j].x);
+    x[8 * j + 2] = bf16_lo(t[j].y); x[8 * j + 3] = bf16_hi(t[j].y);
+    x[8 * j + 4] = bf16_lo(t[j].z); x[8 * j + 5] = bf16_hi(t[j].z);
+    x[8 * j + 6] = bf16_lo(t[j].w); x[8 * j + 7] = bf16_hi(t[j].w);
   }
 }
 __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* p, const float* v) {
@@ -79,40 +79,33 @@ __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* p, const float* v) 
                        pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
 }
 
+template <int EPI>
+constexpr bool epi_has_aux() { return EPI == M3P_EPI_DROP_RES || EPI == M3P_EPI_DGELU || EPI == M3P_EPI_DTANH; }
+
+// sbias: this chunk's 16 bias values in shared memory (staged once per tile, zero past N);
+// auxr : this chunk's aux values (16 bf16), prefetched one chunk ahead when the fast path applies.
 template <int EPI, bool OUT_F32>
-__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const uint32_t* acc,
-                                               long long row, int col0, int ncols) {
+__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const uint32_t* acc, const float* sbias,
+                                               const uint4* auxr, long long row, int col0, int ncols) {
   float v[EW];
   const bool full = (ncols == EW) && p.vec_ok;
   // v = alpha * acc + bias
-  if (p.bias != nullptr) {
-    if (full) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-      for (int j = 0; j < EW / 4; ++j) {
-        const float4 b = __ldg(b4 + j);
-        v[4 * j + 0] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 0]), b.x);
-        v[4 * j + 1] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 1]), b.y);
-        v[4 * j + 2] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 2]), b.z);
-        v[4 * j + 3] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 3]), b.w);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < EW; ++j)
-        v[j] = fmaf(p.alpha, __uint_as_float(acc[j]), (j < ncols) ? __ldg(p.bias + col0 + j) : 0.f);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < EW; ++j) v[j] = p.alpha * __uint_as_float(acc[j]);
+  for (int j = 0; j < EW / 4; ++j) {
+    const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * j);  // broadcast LDS.128
+    v[4 * j + 0] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 0]), b.x);
+    v[4 * j + 1] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 1]), b.y);
+    v[4 * j + 2] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 2]), b.z);
+    v[4 * j + 3] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 3]), b.w);
   }
 
   // auxiliary operand (residual / stashed gelu' / tanh output)
-  if constexpr (EPI == M3P_EPI_DROP_RES || EPI == M3P_EPI_DGELU || EPI == M3P_EPI_DTANH) {
+  if constexpr (epi_has_aux<EPI>()) {
     float x[EW];
-    const __nv_bfloat16* ap = p.aux + row * p.ldaux + col0;
     if (full) {
-      load_bf16x16(ap, x);
+      unpack_bf16x16(auxr, x);
     } else {
+      const __nv_bfloat16* ap = p.aux + row * p.ldaux + col0;
 #pragma unroll
       for (int j = 0; j < EW; ++j) x[j] = (j < ncols) ? __bfloat162float(ap[j]) : 0.f;
     }
@@ -152,13 +145,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
     // (M3P_EPI_DGELU) becomes a plain multiply by the stashed derivative.
     float gq[EW];
 #pragma unroll
-    for (int j = 0; j < EW; ++j) {
-      float e;
-      const float er = erf_as(v[j] * 0.70710678118654752f, &e);
-      const float cdf = fmaf(0.5f, er, 0.5f);
-      gq[j] = v[j] * cdf;
-      v[j] = fmaf(v[j] * e, 0.3989422804014327f, cdf);
-    }
+    for (int j = 0; j < EW; ++j) gelu_and_grad(v[j], gq[j], v[j]);
     __nv_bfloat16* gp = p.out2 + row * p.ldo2 + col0;
     if (full) {
       store_bf16x16(gp, gq);
@@ -184,12 +171,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
           o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
     } else {
-#pragma unroll
-      for (int j = 0; j < EW; ++j) {
-        if (j < ncols) {
-          if (p.accumulate) atomicAdd(op + j, v[j]);
-          else op[j] = v[j];
-        }
+#pragma unroll 1
+      for (int j = 0; j < ncols; ++j) {
+        if (p.accumulate) atomicAdd(op + j, v[j]);
+        else op[j] = v[j];
       }
     }
   } else {
@@ -204,27 +189,34 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
   }
 }
 
-template <int BN>
+// CTA2 = true: the kernel runs as clusters of two CTAs issuing cta_group::2 MMAs on a 256 x BN tile;
+// each CTA stages its own 128 rows of A and its own BN/2 rows of B (32 KB / k-block instead of 48 KB:
+// the 128 x 256 single-CTA tile is bound by the ~64 B/clk L2 -> SM path at ~2/3 of tensor peak).
+template <int BN, bool CTA2>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int BN_LOAD = CTA2 ? BN / 2 : BN;  // B rows this CTA stages per k-block
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = BN_LOAD * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (STAGE_BYTES > 32 * 1024) ? 4 : 6;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t BIAS_BYTES = EPI_WARPS * (BN / 2) * 4;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EPI, bool OUT_F32>
+template <int BN, int EPI, bool OUT_F32, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmKernelParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTA2>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NCTA = CTA2 ? 2 : 1;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* bias_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -232,6 +224,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  // persistent loop over work units: one unit = one (BLOCK_M * NCTA) x BN output tile (x one K split)
+  const int unit0 = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;
+  const int unit_stride = CTA2 ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp_idx == 0 && elect_one()) {
     prefetch_tmap(&tmap_a);
@@ -244,62 +241,71 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], EPI_WARPS * NCTA);  // one arrival per epilogue warp of every CTA of the pair
     }
     fence_barrier_init();
   }
   if (warp_idx == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CTA2) {
+      tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp_idx == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA stages its own halves) =====================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      for (int u = unit0; u < p.num_units; u += unit_stride) {
         int m_tile, n_tile, ks;
         decode_unit(p, u, m_tile, n_tile, ks);
-        const int m0 = m_tile * BLOCK_M, n0 = n_tile * BN;
+        const int m0 = (m_tile * NCTA + (int)cta_rank) * BLOCK_M;
+        const int n0 = n_tile * BN + (int)cta_rank * Cfg::BN_LOAD;
         const int kb0 = ks * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          // the pair's bytes are all counted on the leader's barrier
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * NCTA);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           const int k0 = kb * BLOCK_K;
+          auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+            if constexpr (CTA2) tma_load_2d_2sm(dst, tm, &full_bar[stage], c0, c1);
+            else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
+          };
           if (!p.a_mn) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);
+            load(sa, &tmap_a, k0, m0);
           } else {
 #pragma unroll
-            for (int s = 0; s < BLOCK_M / 64; ++s)
-              tma_load_2d(sa + s * SLAB_BYTES, &tmap_a, &full_bar[stage], m0 + s * 64, k0);
+            for (int s = 0; s < BLOCK_M / 64; ++s) load(sa + s * SLAB_BYTES, &tmap_a, m0 + s * 64, k0);
           }
           if (!p.b_mn) {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+            load(sb, &tmap_b, k0, n0);
           } else {
 #pragma unroll
-            for (int s = 0; s < BN / 64; ++s)
-              tma_load_2d(sb + s * SLAB_BYTES, &tmap_b, &full_bar[stage], n0 + s * 64, k0);
+            for (int s = 0; s < Cfg::BN_LOAD / 64; ++s) load(sb + s * SLAB_BYTES, &tmap_b, n0 + s * 64, k0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp_idx == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
+    // ===================== MMA issuer (the leader CTA's elected thread) =====================
+    if (leader && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      for (int u = unit0; u < p.num_units; u += unit_stride) {
         int m_tile, n_tile, ks;
         decode_unit(p, u, m_tile, n_tile, ks);
         const int kb0 = ks * p.kblocks_per_split;
@@ -316,12 +322,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(a_addr + k * p.a_kstep, p.a_lbo, p.a_sbo);
             const uint64_t bdesc = make_smem_desc(b_addr + k * p.b_kstep, p.b_lbo, p.b_sbo);
-            umma_ss(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CTA2) umma_ss_2sm(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_ss(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable (in both CTAs) once these MMAs retire
+          if constexpr (CTA2) umma_commit_2sm(&empty_bar[stage], 3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc_stage]);  // accumulator complete
+        // accumulator complete (each CTA drains its own 128 rows)
+        if constexpr (CTA2) umma_commit_2sm(&tmem_full[acc_stage], 3);
+        else umma_commit(&tmem_full[acc_stage]);
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
@@ -329,62 +340,123 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ===================== epilogue =====================
     const int q = warp_idx & 3;            // TMEM lane quarter this warp may access
     const int half = (warp_idx - 4) >> 2;  // which half of the tile's columns this warp drains
+    constexpr int NCH = BN / 2 / EW;       // chunks per warp
+    const int cbase = half * (BN / 2);
+    float* sbias = bias_smem + (warp_idx - 4) * (BN / 2);
     int acc_stage = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+    for (int u = unit0; u < p.num_units; u += unit_stride) {
       int m_tile, n_tile, ks;
       decode_unit(p, u, m_tile, n_tile, ks);
       const int n0 = n_tile * BN;
-      const long long row = static_cast<long long>(m_tile) * BLOCK_M + q * 32 + lane;
+      const long long row = static_cast<long long>(m_tile * NCTA + (int)cta_rank) * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      // stage this warp's bias slice (the global loads overlap the wait for the accumulator)
+      for (int c = lane * 4; c < BN / 2; c += 128) {
+        const int col = n0 + cbase + c;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) {
+          if (p.vec_ok && col + 3 < p.N) {
+            b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          } else {
+            if (col + 0 < p.N) b.x = __ldg(p.bias + col + 0);
+            if (col + 1 < p.N) b.y = __ldg(p.bias + col + 1);
+            if (col + 2 < p.N) b.z = __ldg(p.bias + col + 2);
+            if (col + 3 < p.N) b.w = __ldg(p.bias + col + 3);
+          }
+        }
+        *reinterpret_cast<float4*>(sbias + c) = b;
+      }
+      // first chunk of the aux operand, likewise ahead of the accumulator
+      uint4 auxr[2][2];
+      auto aux_fast = [&](int i) { return row_ok && p.vec_ok && (n0 + cbase + i * EW + EW <= p.N); };
+      auto aux_load = [&](int i, uint4* dst) {
+        if constexpr (epi_has_aux<EPI>()) {
+          if (aux_fast(i)) {
+            const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + row * p.ldaux + n0 + cbase + i * EW);
+            dst[0] = __ldg(a4);
+            dst[1] = __ldg(a4 + 1);
+          }
+        }
+      };
+      aux_load(0, auxr[0]);
+      __syncwarp();
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
-      // software-pipelined drain: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed
-      constexpr int NCH = BN / 2 / EW;  // chunks per warp (this warp's half of the tile)
-      const int cbase = half * (BN / 2);
+      // software-pipelined drain: the tcgen05.ld and the aux load of chunk i+1 are in flight while
+      // chunk i is processed
       uint32_t acc[2][EW];
       tmem_ld_32x32b_x16(t_base + cbase, acc[0]);
+#pragma unroll 1
+      for (int i0 = 0; i0 < NCH; i0 += 2) {
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        tmem_ld_wait16(acc[i & 1]);
-        if (i + 1 < NCH) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[(i + 1) & 1]);
-        const int col0 = n0 + cbase + i * EW;
-        if (row < p.M && col0 < p.N)
-          epilogue_chunk<EPI, OUT_F32>(p, acc[i & 1], row, col0, min(EW, p.N - col0));
+        for (int ii = 0; ii < 2; ++ii) {
+          const int i = i0 + ii;
+          tmem_ld_wait16(acc[ii]);
+          if (i + 1 < NCH) {
+            tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
+            aux_load(i + 1, auxr[ii ^ 1]);
+          }
+          const int col0 = n0 + cbase + i * EW;
+          if (row_ok && col0 < p.N)
+            epilogue_chunk<EPI, OUT_F32>(p, acc[ii], sbias + i * EW, auxr[ii], row, col0, min(EW, p.N - col0));
+        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_cluster(&tmem_empty[acc_stage], 0);  // the leader's MMA thread waits on it
+        else mbar_arrive(&tmem_empty[acc_stage]);
+      }
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp_idx == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
+  if (warp_idx == 2) {
+    if constexpr (CTA2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
-template <int BN, int EPI, bool OUT_F32>
+template <int BN, int EPI, bool OUT_F32, bool CTA2>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kfn = gemm_kernel<BN, EPI, OUT_F32>;
+  using Cfg = GemmCfg<BN, CTA2>;
+  auto kfn = gemm_kernel<BN, EPI, OUT_F32, CTA2>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     M3P_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(Cfg::SMEM_BYTES)));
     attr_set = true;
   }
-  const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
-  kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
-  M3P_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  if (CTA2) {
+    const int clusters = p.num_units < sm_count() / 2 ? p.num_units : sm_count() / 2;
+    cfg.gridDim = dim3(2 * clusters);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(p.num_units < sm_count() ? p.num_units : sm_count());
+  }
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  M3P_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, ta, tb, p));
   return M3P_OK;
 }
 
-template <int BN>
+template <int BN, bool CTA2>
 static int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p,
                         int epi, bool out_f32, cudaStream_t s) {
   if (out_f32) {
@@ -392,19 +464,30 @@ static int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
       set_last_error("m3p_gemm_bf16: fp32 output only with M3P_EPI_LINEAR");
       return M3P_ERR_UNSUPPORTED;
     }
-    return launch_gemm<BN, M3P_EPI_LINEAR, true>(ta, tb, p, s);
+    return launch_gemm<BN, M3P_EPI_LINEAR, true, CTA2>(ta, tb, p, s);
   }
   switch (epi) {
-    case M3P_EPI_LINEAR: return launch_gemm<BN, M3P_EPI_LINEAR, false>(ta, tb, p, s);
-    case M3P_EPI_GELU: return launch_gemm<BN, M3P_EPI_GELU, false>(ta, tb, p, s);
-    case M3P_EPI_DROP_RES: return launch_gemm<BN, M3P_EPI_DROP_RES, false>(ta, tb, p, s);
-    case M3P_EPI_DGELU: return launch_gemm<BN, M3P_EPI_DGELU, false>(ta, tb, p, s);
-    case M3P_EPI_TANH: return launch_gemm<BN, M3P_EPI_TANH, false>(ta, tb, p, s);
-    case M3P_EPI_DTANH: return launch_gemm<BN, M3P_EPI_DTANH, false>(ta, tb, p, s);
+    case M3P_EPI_LINEAR: return launch_gemm<BN, M3P_EPI_LINEAR, false, CTA2>(ta, tb, p, s);
+    case M3P_EPI_GELU: return launch_gemm<BN, M3P_EPI_GELU, false, CTA2>(ta, tb, p, s);
+    case M3P_EPI_DROP_RES: return launch_gemm<BN, M3P_EPI_DROP_RES, false, CTA2>(ta, tb, p, s);
+    case M3P_EPI_DGELU: return launch_gemm<BN, M3P_EPI_DGELU, false, CTA2>(ta, tb, p, s);
+    case M3P_EPI_TANH: return launch_gemm<BN, M3P_EPI_TANH, false, CTA2>(ta, tb, p, s);
+    case M3P_EPI_DTANH: return launch_gemm<BN, M3P_EPI_DTANH, false, CTA2>(ta, tb, p, s);
     default:
       set_last_error("m3p_gemm_bf16: unknown epilogue %d", epi);
       return M3P_ERR_INVALID_ARGUMENT;
   }
+}
+
+// CTA pairs (cta_group::2) are the default whenever the problem has more than one 128-row tile;
+// M3P_GEMM_2CTA=0 forces the single-CTA kernel (A/B measurements, bring-up).
+static bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("M3P_GEMM_2CTA");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -430,9 +513,11 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   M3P_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, "m3p_gemm_bf16: drop_p out of range");
 
   const int BN = (a->n > 128) ? 256 : 128;
+  const bool cta2 = use_cta_pairs() && a->m > BLOCK_M;
+  const int tile_m = cta2 ? 2 * BLOCK_M : BLOCK_M;
   GemmKernelParams p{};
   p.M = (int)a->m; p.N = (int)a->n; p.K = (int)a->k;
-  const int num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_m_tiles = (p.M + tile_m - 1) / tile_m;
   p.num_n_tiles = (p.N + BN - 1) / BN;
   p.kblocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   int split = a->split_k < p.kblocks_total ? a->split_k : p.kblocks_total;
@@ -457,7 +542,7 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   if (b_lbo >= 0) p.b_lbo = b_lbo;
   if (b_sbo >= 0) p.b_sbo = b_sbo;
   if (b_kstep >= 0) p.b_kstep = b_kstep;
-  p.idesc = make_idesc_bf16(BLOCK_M, BN, p.a_mn, p.b_mn);
+  p.idesc = make_idesc_bf16(tile_m, BN, p.a_mn, p.b_mn);
   p.alpha = a->alpha;
   p.bias = a->bias;
   p.out = a->out; p.ldo = a->ldo;
@@ -482,12 +567,17 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   if (!p.a_mn) rc = get_tmap_2d_bf16(&ta, a->a, (uint64_t)a->k, (uint64_t)a->m, (uint64_t)a->lda, BLOCK_K, BLOCK_M);
   else         rc = get_tmap_2d_bf16(&ta, a->a, (uint64_t)a->m, (uint64_t)a->k, (uint64_t)a->lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!p.b_mn) rc = get_tmap_2d_bf16(&tb, a->b, (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, BLOCK_K, BN);
+  if (!p.b_mn) rc = get_tmap_2d_bf16(&tb, a->b, (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, BLOCK_K,
+                                     cta2 ? BN / 2 : BN);
   else         rc = get_tmap_2d_bf16(&tb, a->b, (uint64_t)a->n, (uint64_t)a->k, (uint64_t)a->ldb, 64, BLOCK_K);
   if (rc) return rc;
 
-  if (BN == 256) return dispatch_epi<256>(ta, tb, p, a->epilogue, a->out_f32 != 0, stream);
-  return dispatch_epi<128>(ta, tb, p, a->epilogue, a->out_f32 != 0, stream);
+  if (cta2) {
+    if (BN == 256) return dispatch_epi<256, true>(ta, tb, p, a->epilogue, a->out_f32 != 0, stream);
+    return dispatch_epi<128, true>(ta, tb, p, a->epilogue, a->out_f32 != 0, stream);
+  }
+  if (BN == 256) return dispatch_epi<256, false>(ta, tb, p, a->epilogue, a->out_f32 != 0, stream);
+  return dispatch_epi<128, false>(ta, tb, p, a->epilogue, a->out_f32 != 0, stream);
 }
 
 }  // namespace m3p
