@@ -48,6 +48,7 @@ struct GemmKernelParams {
   uint32_t thr16, seed_lo, seed_hi;
   int accumulate;
   int vec_ok;  // all pitches / bases allow 16-byte vector access
+  int tma_store;  // bf16 outputs leave through smem staging + cp.async.bulk.tensor stores
 };
 
 __device__ __forceinline__ void decode_unit(const GemmKernelParams& p, int u, int& m_tile,
@@ -84,9 +85,23 @@ constexpr bool epi_has_aux() { return EPI == M3P_EPI_DROP_RES || EPI == M3P_EPI_
 
 // sbias: this chunk's 16 bias values in shared memory (staged once per tile, zero past N);
 // auxr : this chunk's aux values (16 bf16), prefetched one chunk ahead when the fast path applies.
+// 16 bf16 of one row into a [32 rows][128 B] SWIZZLE_128B staging tile (the layout a TMA store expects):
+// 16-byte chunk c16 of row r lives at r*128 + ((c16 ^ (r & 7)) << 4) — conflict-free for a warp.
+__device__ __forceinline__ void stage_bf16x16(uint8_t* stg, int r, int chunk_in_group, const float* v) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c16 = chunk_in_group * 2 + h;
+    *reinterpret_cast<uint4*>(stg + r * 128 + ((c16 ^ (r & 7)) << 4)) =
+        make_uint4(pack_bf16x2(v[8 * h + 0], v[8 * h + 1]), pack_bf16x2(v[8 * h + 2], v[8 * h + 3]),
+                   pack_bf16x2(v[8 * h + 4], v[8 * h + 5]), pack_bf16x2(v[8 * h + 6], v[8 * h + 7]));
+  }
+}
+
+// stg / stg2 != nullptr: bf16 results go to the warp's staging tiles (TMA-store path) instead of global.
 template <int EPI, bool OUT_F32>
 __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const uint32_t* acc, const float* sbias,
-                                               const uint4* auxr, long long row, int col0, int ncols) {
+                                               const uint4* auxr, long long row, int col0, int ncols,
+                                               uint8_t* stg, uint8_t* stg2, int lane, int chunk_in_group) {
   float v[EW];
   const bool full = (ncols == EW) && p.vec_ok;
   // v = alpha * acc + bias
@@ -147,7 +162,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
 #pragma unroll
     for (int j = 0; j < EW; ++j) gelu_and_grad(v[j], gq[j], v[j]);
     __nv_bfloat16* gp = p.out2 + row * p.ldo2 + col0;
-    if (full) {
+    if (stg2 != nullptr) {
+      stage_bf16x16(stg2, lane, chunk_in_group, gq);
+    } else if (full) {
       store_bf16x16(gp, gq);
     } else {
 #pragma unroll
@@ -171,15 +188,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
           o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
     } else {
-#pragma unroll 1
-      for (int j = 0; j < ncols; ++j) {
-        if (p.accumulate) atomicAdd(op + j, v[j]);
-        else op[j] = v[j];
+#pragma unroll
+      for (int j = 0; j < EW; ++j) {
+        if (j < ncols) {
+          if (p.accumulate) atomicAdd(op + j, v[j]);
+          else op[j] = v[j];
+        }
       }
     }
   } else {
     __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
-    if (full) {
+    if (stg != nullptr) {
+      stage_bf16x16(stg, lane, chunk_in_group, v);
+    } else if (full) {
       store_bf16x16(op, v);
     } else {
 #pragma unroll
@@ -192,31 +213,39 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
 // CTA2 = true: the kernel runs as clusters of two CTAs issuing cta_group::2 MMAs on a 256 x BN tile;
 // each CTA stages its own 128 rows of A and its own BN/2 rows of B (32 KB / k-block instead of 48 KB:
 // the 128 x 256 single-CTA tile is bound by the ~64 B/clk L2 -> SM path at ~2/3 of tensor peak).
-template <int BN, bool CTA2>
+template <int BN, bool CTA2, int EPI, bool OUT_F32>
 struct GemmCfg {
   static constexpr int BN_LOAD = CTA2 ? BN / 2 : BN;  // B rows this CTA stages per k-block
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = BN_LOAD * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (STAGE_BYTES > 32 * 1024) ? 4 : 6;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
   static constexpr uint32_t BIAS_BYTES = EPI_WARPS * (BN / 2) * 4;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // output staging for the TMA-store epilogue: one [32 rows][64 cols] bf16 tile per warp per output
+  static constexpr int N_OUT = OUT_F32 ? 0 : (EPI == M3P_EPI_GELU ? 2 : 1);
+  static constexpr uint32_t STG_TILE = 32 * 128;
+  static constexpr uint32_t STG_BYTES = EPI_WARPS * N_OUT * STG_TILE;
+  static constexpr uint32_t BUDGET = 200 * 1024;
+  static constexpr int STAGES_FIT = (BUDGET - STG_BYTES - BIAS_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int BN, int EPI, bool OUT_F32, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
             const GemmKernelParams p) {
-  using Cfg = GemmCfg<BN, CTA2>;
+  using Cfg = GemmCfg<BN, CTA2, EPI, OUT_F32>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NCTA = CTA2 ? 2 : 1;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  float* bias_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BIAS_BYTES);
+  uint8_t* stg_smem = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned: STAGE_BYTES is a multiple of 1024
+  float* bias_smem = reinterpret_cast<float*>(stg_smem + Cfg::STG_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES + Cfg::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -233,6 +262,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp_idx == 0 && elect_one()) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (p.tma_store) {
+      prefetch_tmap(&tmap_o);
+      if constexpr (EPI == M3P_EPI_GELU) prefetch_tmap(&tmap_o2);
+    }
   }
   if (warp_idx == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) {
@@ -367,40 +400,68 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         *reinterpret_cast<float4*>(sbias + c) = b;
       }
-      // first chunk of the aux operand, likewise ahead of the accumulator
-      uint4 auxr[2][2];
-      auto aux_fast = [&](int i) { return row_ok && p.vec_ok && (n0 + cbase + i * EW + EW <= p.N); };
-      auto aux_load = [&](int i, uint4* dst) {
-        if constexpr (epi_has_aux<EPI>()) {
-          if (aux_fast(i)) {
+      // the whole aux slice of this thread's row (residual / stashed gelu'), likewise ahead of the
+      // accumulator: its latency hides behind the tile's main loop
+      constexpr bool HAS_AUX = epi_has_aux<EPI>();
+      constexpr int NAUX = HAS_AUX ? NCH : 1;
+      uint4 auxr[NAUX][2];
+      if constexpr (HAS_AUX) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          if (row_ok && p.vec_ok && (n0 + cbase + i * EW + EW <= p.N)) {
             const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + row * p.ldaux + n0 + cbase + i * EW);
-            dst[0] = __ldg(a4);
-            dst[1] = __ldg(a4 + 1);
+            auxr[i][0] = __ldg(a4);
+            auxr[i][1] = __ldg(a4 + 1);
           }
         }
-      };
-      aux_load(0, auxr[0]);
+      }
       __syncwarp();
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
-      // software-pipelined drain: the tcgen05.ld and the aux load of chunk i+1 are in flight while
-      // chunk i is processed
+      const bool use_tma = (!OUT_F32) && p.tma_store;
+      uint8_t* stg = use_tma ? stg_smem + (warp_idx - 4) * Cfg::N_OUT * Cfg::STG_TILE : nullptr;
+      uint8_t* stg2 = (use_tma && EPI == M3P_EPI_GELU) ? stg + Cfg::STG_TILE : nullptr;
+      const int row0 = (m_tile * NCTA + (int)cta_rank) * BLOCK_M + q * 32;  // first row of this warp's sub-tile
+      // software-pipelined drain: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed;
+      // every 4 chunks (64 columns) the warp's staging tile leaves through one TMA store
       uint32_t acc[2][EW];
       tmem_ld_32x32b_x16(t_base + cbase, acc[0]);
-#pragma unroll 1
-      for (int i0 = 0; i0 < NCH; i0 += 2) {
-#pragma unroll
-        for (int ii = 0; ii < 2; ++ii) {
-          const int i = i0 + ii;
-          tmem_ld_wait16(acc[ii]);
-          if (i + 1 < NCH) {
-            tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
-            aux_load(i + 1, auxr[ii ^ 1]);
+      auto chunk = [&](int i, int ii, const uint4* ax) {
+        tmem_ld_wait16(acc[ii]);
+        if (i + 1 < NCH) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
+        const int col0 = n0 + cbase + i * EW;
+        if (use_tma) {
+          if ((i & 3) == 0) {  // staging tile must have been read by the previous group's TMA store
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
           }
-          const int col0 = n0 + cbase + i * EW;
+          // rows / columns outside the problem are clipped by the TMA store; skip their math (and aux reads)
           if (row_ok && col0 < p.N)
-            epilogue_chunk<EPI, OUT_F32>(p, acc[ii], sbias + i * EW, auxr[ii], row, col0, min(EW, p.N - col0));
+            epilogue_chunk<EPI, OUT_F32>(p, acc[ii], sbias + i * EW, ax, row, col0, min(EW, p.N - col0), stg, stg2,
+                                         lane, i & 3);
+          if ((i & 3) == 3) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && col0 - 3 * EW < p.N && row0 < p.M) {
+              tma_store_2d(&tmap_o, stg, col0 - 3 * EW, row0);
+              if constexpr (EPI == M3P_EPI_GELU) tma_store_2d(&tmap_o2, stg2, col0 - 3 * EW, row0);
+              tma_store_commit();
+            }
+          }
+        } else if (row_ok && col0 < p.N) {
+          epilogue_chunk<EPI, OUT_F32>(p, acc[ii], sbias + i * EW, ax, row, col0, min(EW, p.N - col0), nullptr,
+                                       nullptr, lane, 0);
+        }
+      };
+      if constexpr (HAS_AUX) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) chunk(i, i & 1, auxr[i]);
+      } else {
+#pragma unroll 1
+        for (int i0 = 0; i0 < NCH; i0 += 2) {
+          chunk(i0, 0, auxr[0]);
+          chunk(i0 + 1, 1, auxr[0]);
         }
       }
       tc_fence_before();
@@ -411,6 +472,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait<0>();  // smem must outlive the bulk stores that read it
   }
 
   tc_fence_before();
@@ -425,9 +487,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // host launcher
 // ---------------------------------------------------------------------------------------------
 template <int BN, int EPI, bool OUT_F32, bool CTA2>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p,
-                       cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CTA2>;
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                       const GemmKernelParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CTA2, EPI, OUT_F32>;
   auto kfn = gemm_kernel<BN, EPI, OUT_F32, CTA2>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -452,27 +514,27 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  M3P_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, ta, tb, p));
+  M3P_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, ta, tb, to, to2, p));
   return M3P_OK;
 }
 
 template <int BN, bool CTA2>
-static int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p,
-                        int epi, bool out_f32, cudaStream_t s) {
+static int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                        const GemmKernelParams& p, int epi, bool out_f32, cudaStream_t s) {
   if (out_f32) {
     if (epi != M3P_EPI_LINEAR) {
       set_last_error("m3p_gemm_bf16: fp32 output only with M3P_EPI_LINEAR");
       return M3P_ERR_UNSUPPORTED;
     }
-    return launch_gemm<BN, M3P_EPI_LINEAR, true, CTA2>(ta, tb, p, s);
+    return launch_gemm<BN, M3P_EPI_LINEAR, true, CTA2>(ta, tb, to, to2, p, s);
   }
   switch (epi) {
-    case M3P_EPI_LINEAR: return launch_gemm<BN, M3P_EPI_LINEAR, false, CTA2>(ta, tb, p, s);
-    case M3P_EPI_GELU: return launch_gemm<BN, M3P_EPI_GELU, false, CTA2>(ta, tb, p, s);
-    case M3P_EPI_DROP_RES: return launch_gemm<BN, M3P_EPI_DROP_RES, false, CTA2>(ta, tb, p, s);
-    case M3P_EPI_DGELU: return launch_gemm<BN, M3P_EPI_DGELU, false, CTA2>(ta, tb, p, s);
-    case M3P_EPI_TANH: return launch_gemm<BN, M3P_EPI_TANH, false, CTA2>(ta, tb, p, s);
-    case M3P_EPI_DTANH: return launch_gemm<BN, M3P_EPI_DTANH, false, CTA2>(ta, tb, p, s);
+    case M3P_EPI_LINEAR: return launch_gemm<BN, M3P_EPI_LINEAR, false, CTA2>(ta, tb, to, to2, p, s);
+    case M3P_EPI_GELU: return launch_gemm<BN, M3P_EPI_GELU, false, CTA2>(ta, tb, to, to2, p, s);
+    case M3P_EPI_DROP_RES: return launch_gemm<BN, M3P_EPI_DROP_RES, false, CTA2>(ta, tb, to, to2, p, s);
+    case M3P_EPI_DGELU: return launch_gemm<BN, M3P_EPI_DGELU, false, CTA2>(ta, tb, to, to2, p, s);
+    case M3P_EPI_TANH: return launch_gemm<BN, M3P_EPI_TANH, false, CTA2>(ta, tb, to, to2, p, s);
+    case M3P_EPI_DTANH: return launch_gemm<BN, M3P_EPI_DTANH, false, CTA2>(ta, tb, to, to2, p, s);
     default:
       set_last_error("m3p_gemm_bf16: unknown epilogue %d", epi);
       return M3P_ERR_INVALID_ARGUMENT;
@@ -481,6 +543,14 @@ static int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
 
 // CTA pairs (cta_group::2) are the default whenever the problem has more than one 128-row tile;
 // M3P_GEMM_2CTA=0 forces the single-CTA kernel (A/B measurements, bring-up).
+static bool use_tma_store() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("M3P_GEMM_TMA_STORE");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 static bool use_cta_pairs() {
   static int v = -1;
   if (v < 0) {
@@ -572,12 +642,23 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   else         rc = get_tmap_2d_bf16(&tb, a->b, (uint64_t)a->n, (uint64_t)a->k, (uint64_t)a->ldb, 64, BLOCK_K);
   if (rc) return rc;
 
-  if (cta2) {
-    if (BN == 256) return dispatch_epi<256, true>(ta, tb, p, a->epilogue, a->out_f32 != 0, stream);
-    return dispatch_epi<128, true>(ta, tb, p, a->epilogue, a->out_f32 != 0, stream);
+  // bf16 outputs: [32 rows][64 cols] boxes for the TMA-store epilogue
+  CUtensorMap to = ta, to2 = ta;
+  p.tma_store = (!a->out_f32 && p.vec_ok && use_tma_store()) ? 1 : 0;
+  if (p.tma_store) {
+    rc = get_tmap_2d_bf16(&to, a->out, (uint64_t)a->n, (uint64_t)a->m, (uint64_t)a->ldo, 64, 32);
+    if (rc) return rc;
+    if (a->epilogue == M3P_EPI_GELU) {
+      rc = get_tmap_2d_bf16(&to2, a->out2, (uint64_t)a->n, (uint64_t)a->m, (uint64_t)a->ldo2, 64, 32);
+      if (rc) return rc;
+    }
   }
-  if (BN == 256) return dispatch_epi<256, false>(ta, tb, p, a->epilogue, a->out_f32 != 0, stream);
-  return dispatch_epi<128, false>(ta, tb, p, a->epilogue, a->out_f32 != 0, stream);
+  if (cta2) {
+    if (BN == 256) return dispatch_epi<256, true>(ta, tb, to, to2, p, a->epilogue, a->out_f32 != 0, stream);
+    return dispatch_epi<128, true>(ta, tb, to, to2, p, a->epilogue, a->out_f32 != 0, stream);
+  }
+  if (BN == 256) return dispatch_epi<256, false>(ta, tb, to, to2, p, a->epilogue, a->out_f32 != 0, stream);
+  return dispatch_epi<128, false>(ta, tb, to, to2, p, a->epilogue, a->out_f32 != 0, stream);
 }
 
 }  // namespace m3p
