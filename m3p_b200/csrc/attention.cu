@@ -65,9 +65,12 @@ __device__ __forceinline__ uint32_t attn_drop_base(int bh, int q, int key0) {
 // forward
 // =================================================================================================
 constexpr uint32_t FWD_SMEM_TILES = 96 * 1024;  // sQ 16K | sK 32K | pad 16K | sV 32K ; sP aliases first 64K
-constexpr uint32_t FWD_SMEM_BYTES = FWD_SMEM_TILES + 64 + 1024;
+constexpr uint32_t FWD_SMEM_BYTES = FWD_SMEM_TILES + 2 * 2 * 128 * 4 + 64 + 1024;
+constexpr int FWD_THREADS = 256;
 
-__global__ void __launch_bounds__(128, 2)
+// 256 threads: two threads per query row, each owning every other 32-key chunk (even / odd), so four
+// warps per scheduler hide the exp / max dependency chains; row max and sum are exchanged through smem.
+__global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                 const AttnKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -77,7 +80,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sK = smem + 16 * 1024;
   uint8_t* sV = smem + 64 * 1024;
   uint8_t* sP = smem;  // written only after the score MMA has consumed sQ / sK
-  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + FWD_SMEM_TILES);
+  float* s_max = reinterpret_cast<float*>(smem + FWD_SMEM_TILES);  // [2][128]
+  float* s_sum = s_max + 2 * 128;                                  // [2][128]
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(s_sum + 2 * 128);
   uint64_t* bar_v = bar_qk + 1;
   uint64_t* bar_s = bar_qk + 2;
   uint64_t* bar_o = bar_qk + 3;
@@ -85,6 +90,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int w4 = warp & 3, half = warp >> 2;
   const int u = blockIdx.x;
   const int mt = u % p.MT;
   const int h = (u / p.MT) % p.H;
@@ -129,36 +135,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncwarp();
   tc_fence_after();
 
-  // ---- softmax: one thread per query row ----
+  // ---- softmax ----
   // Interior 32-key chunks (entirely below the key length L) take a path without per-element masking;
   // only the chunk that straddles L pays for the compares.  The dropout scale 1/(1-p) is folded into
   // the final 1/sum normalisation, so a dropped weight is a plain select-to-zero.
-  const int row = warp * 32 + lane;
+  const int row = w4 * 32 + lane;
   const int q_idx = mt * 128 + row;
   int L = p.seqlen[b];
   L = L < 0 ? 0 : (L > p.S ? p.S : L);
-  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
   const int nchunk = (p.n_kv + 31) >> 5;
   const int nfull = L >> 5;  // chunks with every key valid
-  float mx = -INFINITY;
-  for (int c = 0; c < nchunk; ++c) {
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  for (int c = half; c < nchunk; c += 2) {
     if (c * 32 >= L) break;
     uint32_t acc[32];
     tmem_ld_32x32b_x32(t_row + c * 32, acc);
     tmem_ld_wait();
     if (c < nfull) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(acc[j]));
+      for (int j = 0; j < 32; j += 2) {
+        mx0 = fmaxf(mx0, __uint_as_float(acc[j]));
+        mx1 = fmaxf(mx1, __uint_as_float(acc[j + 1]));
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (c * 32 + j < L) mx = fmaxf(mx, __uint_as_float(acc[j]));
+        if (c * 32 + j < L) mx0 = fmaxf(mx0, __uint_as_float(acc[j]));
     }
   }
+  s_max[half * 128 + row] = fmaxf(mx0, mx1);
+  __syncthreads();
+  const float mx = fmaxf(s_max[row], s_max[128 + row]);
   const float mxs = (L > 0) ? mx * p.scale_log2 : 0.f;
-  float sum = 0.f;
+  float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
   const int bh = b * p.H + h;
-  for (int c = 0; c < nchunk; ++c) {
+  for (int c = half; c < nchunk; c += 2) {
     float pv[32];
     if (c * 32 < L) {
       uint32_t acc[32];
@@ -166,16 +178,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_ld_wait();
       if (c < nfull) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          pv[j] = ex2(fmaf(__uint_as_float(acc[j]), p.scale_log2, -mxs));
-          sum += pv[j];
+        for (int j = 0; j < 32; j += 4) {
+          pv[j + 0] = ex2(fmaf(__uint_as_float(acc[j + 0]), p.scale_log2, -mxs));
+          pv[j + 1] = ex2(fmaf(__uint_as_float(acc[j + 1]), p.scale_log2, -mxs));
+          pv[j + 2] = ex2(fmaf(__uint_as_float(acc[j + 2]), p.scale_log2, -mxs));
+          pv[j + 3] = ex2(fmaf(__uint_as_float(acc[j + 3]), p.scale_log2, -mxs));
+          sum0 += pv[j + 0]; sum1 += pv[j + 1]; sum2 += pv[j + 2]; sum3 += pv[j + 3];
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float e = ex2(fmaf(__uint_as_float(acc[j]), p.scale_log2, -mxs));
           pv[j] = (c * 32 + j < L) ? e : 0.f;
-          sum += pv[j];
+          sum0 += pv[j];
         }
       }
       if (p.thr16 != 0) {
@@ -200,6 +215,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       *reinterpret_cast<uint4*>(blk + swz_off(row, (c & 1) * 4 + g)) = v;
     }
   }
+  s_sum[half * 128 + row] = (sum0 + sum1) + (sum2 + sum3);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -217,6 +233,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     umma_commit(bar_o);
   }
+  const float sum = s_sum[row] + s_sum[128 + row];
   __syncwarp();
   mbar_wait(bar_o, 0);
   __syncwarp();
@@ -224,12 +241,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   {
     const float inv = sum > 0.f ? p.drop_scale / sum : 0.f;  // dropout's 1/(1-p) folded in here
-    uint32_t o0[32], o1[32];
-    tmem_ld_32x32b_x32(t_row, o0);
-    tmem_ld_32x32b_x32(t_row + 32, o1);
+    uint32_t o0[32];
+    tmem_ld_32x32b_x32(t_row + half * 32, o0);  // this thread's 32 of the 64 output columns
     tmem_ld_wait();
     if (q_idx < p.S) {
-      __nv_bfloat16* op = p.ctx + (static_cast<long long>(b) * p.S + q_idx) * p.d + h * ATT_DH;
+      __nv_bfloat16* op = p.ctx + (static_cast<long long>(b) * p.S + q_idx) * p.d + h * ATT_DH + half * 32;
       uint4* o4 = reinterpret_cast<uint4*>(op);
 #pragma unroll
       for (int g = 0; g < 4; ++g)
@@ -237,13 +253,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                            pack_bf16x2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
                            pack_bf16x2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
                            pack_bf16x2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv));
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        o4[4 + g] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * g + 0]) * inv, __uint_as_float(o1[8 * g + 1]) * inv),
-                               pack_bf16x2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv),
-                               pack_bf16x2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv),
-                               pack_bf16x2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv));
-      p.lse[(static_cast<long long>(bh)) * p.S + q_idx] = (sum > 0.f) ? mxs + log2f(sum) : INFINITY;
+      if (half == 0) p.lse[(static_cast<long long>(bh)) * p.S + q_idx] = (sum > 0.f) ? mxs + log2f(sum) : INFINITY;
     }
   }
   tc_fence_before();
@@ -271,7 +281,7 @@ __device__ __forceinline__ void store_acc32(__nv_bfloat16* dst, const uint32_t* 
 
 __global__ void __launch_bounds__(256, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                const AttnKernelParams p) {
+                const __grid_constant__ CUtensorMap tmap_o, const AttnKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -297,6 +307,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_qkv);
     prefetch_tmap(&tmap_do);
+    prefetch_tmap(&tmap_o);
     mbar_init(bar_ld, 1);
     mbar_init(bar_sd, 1);
     mbar_init(bar_g, 1);
@@ -312,35 +323,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar_ld, 4 * 32 * 1024);
+    // Q, K, V, dO and (temporarily, in the P staging buffer) the forward output O
+    mbar_arrive_expect_tx(bar_ld, 5 * 32 * 1024);
     tma_load_3d(sQ, &tmap_qkv, bar_ld, h * ATT_DH, 0, b);
     tma_load_3d(sK, &tmap_qkv, bar_ld, p.d + h * ATT_DH, 0, b);
     tma_load_3d(sV, &tmap_qkv, bar_ld, 2 * p.d + h * ATT_DH, 0, b);
     tma_load_3d(sdO, &tmap_do, bar_ld, h * ATT_DH, 0, b);
+    tma_load_3d(sP, &tmap_o, bar_ld, h * ATT_DH, 0, b);
   }
-
-  // ---- delta = rowsum(dO * O), lse: one thread per query row (global reads overlap the TMA) ----
   {
     const int r = threadIdx.x;
-    float dl = 0.f, ls = INFINITY;  // phantom query rows: exp2(s - inf) = 0, no per-element test needed
-    if (r < p.S) {
-      const long long off = (static_cast<long long>(b) * p.S + r) * p.d + h * ATT_DH;
-      const uint4* a4 = reinterpret_cast<const uint4*>(p.dctx + off);
-      const uint4* o4 = reinterpret_cast<const uint4*>(p.ctx_in + off);
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint4 a = __ldg(a4 + g), o = __ldg(o4 + g);
-        dl = fmaf(bf16_lo(a.x), bf16_lo(o.x), dl); dl = fmaf(bf16_hi(a.x), bf16_hi(o.x), dl);
-        dl = fmaf(bf16_lo(a.y), bf16_lo(o.y), dl); dl = fmaf(bf16_hi(a.y), bf16_hi(o.y), dl);
-        dl = fmaf(bf16_lo(a.z), bf16_lo(o.z), dl); dl = fmaf(bf16_hi(a.z), bf16_hi(o.z), dl);
-        dl = fmaf(bf16_lo(a.w), bf16_lo(o.w), dl); dl = fmaf(bf16_hi(a.w), bf16_hi(o.w), dl);
-      }
-      ls = p.lse[static_cast<long long>(bh) * p.S + r];
-    }
-    s_delta[r] = dl;
-    s_lse[r] = ls;
+    s_lse[r] = (r < p.S) ? p.lse[static_cast<long long>(bh) * p.S + r] : INFINITY;  // phantom rows: exp2(-inf) = 0
   }
-  __syncthreads();
+  __syncwarp();
+  mbar_wait(bar_ld, 0);
+  __syncwarp();
 
   int L = p.seqlen[b];
   L = L < 0 ? 0 : (L > p.S ? p.S : L);
@@ -370,10 +367,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     umma_commit(bar_sd);
   };
 
-  if (threadIdx.x == 0) {
-    mbar_wait(bar_ld, 0);
-    issue_s_dp(0, 0);
+  if (threadIdx.x == 0) issue_s_dp(0, 0);  // runs on the tensor pipe while delta is computed below
+  // ---- delta = rowsum(dO * O) from the TMA-staged (128B-swizzled) tiles: one thread per query row ----
+  {
+    const int r = threadIdx.x;
+    const uint8_t* dob = sdO + (r >> 7) * TILE16K;
+    const uint8_t* ob = sP + (r >> 7) * TILE16K;
+    float dl0 = 0.f, dl1 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint32_t off = swz_off(r & 127, g);
+      const uint4 a = *reinterpret_cast<const uint4*>(dob + off);
+      const uint4 o = *reinterpret_cast<const uint4*>(ob + off);
+      dl0 = fmaf(bf16_lo(a.x), bf16_lo(o.x), dl0); dl1 = fmaf(bf16_hi(a.x), bf16_hi(o.x), dl1);
+      dl0 = fmaf(bf16_lo(a.y), bf16_lo(o.y), dl0); dl1 = fmaf(bf16_hi(a.y), bf16_hi(o.y), dl1);
+      dl0 = fmaf(bf16_lo(a.z), bf16_lo(o.z), dl0); dl1 = fmaf(bf16_hi(a.z), bf16_hi(o.z), dl1);
+      dl0 = fmaf(bf16_lo(a.w), bf16_lo(o.w), dl0); dl1 = fmaf(bf16_hi(a.w), bf16_hi(o.w), dl1);
+    }
+    s_delta[r] = dl0 + dl1;
   }
+  __syncthreads();  // s_delta / s_lse visible; O has been consumed before the first P tile overwrites it
   const int nblocks = NT * NT;
   for (int n = 0; n < nblocks; ++n) {
     const int j = n / NT, i = n % NT;
@@ -569,7 +582,7 @@ extern "C" int m3p_attention_fwd(const m3p_attn_args* a, m3p_stream_t stream_) {
     M3P_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_BYTES));
     attr_set = true;
   }
-  attn_fwd_kernel<<<p.B * p.H * p.MT, 128, FWD_SMEM_BYTES, stream>>>(tq, tkv, p);
+  attn_fwd_kernel<<<p.B * p.H * p.MT, FWD_THREADS, FWD_SMEM_BYTES, stream>>>(tq, tkv, p);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }
@@ -580,18 +593,20 @@ extern "C" int m3p_attention_bwd(const m3p_attn_args* a, m3p_stream_t stream_) {
   int rc = fill_params(a, p, "m3p_attention_bwd");
   if (rc) return rc;
   M3P_REQUIRE(a->dctx && a->dqkv, "m3p_attention_bwd: dctx / dqkv missing");
-  CUtensorMap tqkv, tdo;
+  CUtensorMap tqkv, tdo, to;
   const uint64_t d3 = 3ull * p.d, d1 = (uint64_t)p.d;
   rc = get_tmap_3d_bf16(&tqkv, a->qkv, d3, (uint64_t)p.S, (uint64_t)p.B, d3, d3 * p.S, ATT_DH, 256, 1);
   if (rc) return rc;
   rc = get_tmap_3d_bf16(&tdo, a->dctx, d1, (uint64_t)p.S, (uint64_t)p.B, d1, d1 * p.S, ATT_DH, 256, 1);
+  if (rc) return rc;
+  rc = get_tmap_3d_bf16(&to, a->ctx, d1, (uint64_t)p.S, (uint64_t)p.B, d1, d1 * p.S, ATT_DH, 256, 1);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     M3P_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
     attr_set = true;
   }
-  attn_bwd_kernel<<<p.B * p.H, 256, BWD_SMEM_BYTES, stream>>>(tqkv, tdo, p);
+  attn_bwd_kernel<<<p.B * p.H, 256, BWD_SMEM_BYTES, stream>>>(tqkv, tdo, to, p);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }
