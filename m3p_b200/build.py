@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
     "-I", "/usr/local/graft",  # cudaTypedefs.h fallback location on this image
-]
+] + os.environ.get("M3P_NVCC_EXTRA", "").split()  # e.g. -DM3P_ATTN_TRACE for the phase-timing printfs
 
 
 def _sources():

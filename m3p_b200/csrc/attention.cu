@@ -25,6 +25,22 @@
 
 namespace m3p {
 
+// Phase timing for kernel bring-up: build with M3P_NVCC_EXTRA=-DM3P_ATTN_TRACE and a few CTAs print the
+// SM-clock stamps of their phases (never compiled into the product build).
+#ifdef M3P_ATTN_TRACE
+#define TRACE_DECL long long _t[16]; int _nt = 0;
+#define TRACE_MARK() do { if (threadIdx.x == 0 && _nt < 16) _t[_nt++] = clock64(); } while (0)
+#define TRACE_DUMP(name) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 3 || blockIdx.x == 300 || blockIdx.x == 700)) { \
+    for (int _i = _nt; _i < 16; ++_i) _t[_i] = _t[_nt - 1]; \
+    printf(name " cta %d: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", (int)blockIdx.x, \
+      _t[1]-_t[0], _t[2]-_t[1], _t[3]-_t[2], _t[4]-_t[3], _t[5]-_t[4], _t[6]-_t[5], _t[7]-_t[6], _t[8]-_t[7], _t[9]-_t[8], \
+      _t[10]-_t[9], _t[11]-_t[10], _t[12]-_t[11], _t[13]-_t[12], _t[14]-_t[13], _t[15]-_t[14]); } } while (0)
+#else
+#define TRACE_DECL
+#define TRACE_MARK()
+#define TRACE_DUMP(name)
+#endif
+
 constexpr int ATT_DH = 64;
 constexpr int ATT_MAX_S = 256;
 constexpr uint32_t TILE16K = 128 * 128;  // [128 rows][128 B]
@@ -88,6 +104,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* bar_o = bar_qk + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 4);
 
+  TRACE_DECL
+  TRACE_MARK();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int w4 = warp & 3, half = warp >> 2;
@@ -130,10 +148,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               k > 0 ? 1u : 0u);
     umma_commit(bar_s);
   }
+  TRACE_MARK();  // setup + TMA issue (+ thread 0: wait Q,K and issue S MMA)
   __syncwarp();
   mbar_wait(bar_s, 0);
   __syncwarp();
   tc_fence_after();
+  TRACE_MARK();  // S ready
 
   // ---- softmax ----
   // Interior 32-key chunks (entirely below the key length L) take a path without per-element masking;
@@ -166,6 +186,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
   s_max[half * 128 + row] = fmaxf(mx0, mx1);
   __syncthreads();
+  TRACE_MARK();  // pass 1 (max)
   const float mx = fmaxf(s_max[row], s_max[128 + row]);
   const float mxs = (L > 0) ? mx * p.scale_log2 : 0.f;
   float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
@@ -219,6 +240,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  TRACE_MARK();  // pass 2 (exp, P -> smem)
 
   if (threadIdx.x == 0) {
     tc_fence_after();
@@ -238,6 +260,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   mbar_wait(bar_o, 0);
   __syncwarp();
   tc_fence_after();
+  TRACE_MARK();  // PV MMA done
 
   {
     const float inv = sum > 0.f ? p.drop_scale / sum : 0.f;  // dropout's 1/(1-p) folded in here
@@ -258,6 +281,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  TRACE_MARK();  // epilogue
+  TRACE_DUMP("fwd");
   if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
@@ -298,6 +323,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint64_t* bar_g = bar_ld + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ld + 3);
 
+  TRACE_DECL
+  TRACE_MARK();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int h = blockIdx.x % p.H;
@@ -335,9 +362,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const int r = threadIdx.x;
     s_lse[r] = (r < p.S) ? p.lse[static_cast<long long>(bh) * p.S + r] : INFINITY;  // phantom rows: exp2(-inf) = 0
   }
+  TRACE_MARK();  // setup
   __syncwarp();
   mbar_wait(bar_ld, 0);
   __syncwarp();
+  TRACE_MARK();  // loads landed
 
   int L = p.seqlen[b];
   L = L < 0 ? 0 : (L > p.S ? p.S : L);
@@ -387,6 +416,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     s_delta[r] = dl0 + dl1;
   }
   __syncthreads();  // s_delta / s_lse visible; O has been consumed before the first P tile overwrites it
+  TRACE_MARK();  // delta
   const int nblocks = NT * NT;
   for (int n = 0; n < nblocks; ++n) {
     const int j = n / NT, i = n % NT;
@@ -395,6 +425,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     ph_sd ^= 1;
     __syncwarp();
     tc_fence_after();
+    TRACE_MARK();  // S, dP ready
 
     // ---- P and dS for this thread's row x 64 keys, kept packed in registers ----
     const int q = i * 128 + row;
@@ -413,31 +444,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) { pd[jj] = 0.f; ds[jj] = 0.f; }
       } else {
-        const bool interior = key0 + 32 <= L;
+        // P (normalised: the forward's log2-sum-exp is subtracted inside the exponent)
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) pd[jj] = ex2(fmaf(__uint_as_float(sacc[jj]), p.scale_log2, -lse2));
+        if (key0 + 32 > L) {  // the one chunk that straddles the key length
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) pd[jj] = (key0 + jj < L) ? pd[jj] : 0.f;
+        }
         if (p.thr16 != 0) {
-          const uint32_t e0 = attn_drop_base(bh, q, key0);
+          const uint32_t e0 = attn_drop_base(bh, q, key0) >> 1;
 #pragma unroll
           for (int jp = 0; jp < 16; ++jp) {
-            const uint32_t hsh = drop_hash((e0 >> 1) + jp, p.seed_lo, p.seed_hi);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const int jj = 2 * jp + t;
-              const uint32_t hv = t ? (hsh >> 16) : (hsh & 0xffffu);
-              const float ks = (hv >= p.thr16) ? p.drop_scale : 0.f;
-              float pr = ex2(fmaf(__uint_as_float(sacc[jj]), p.scale_log2, -lse2));
-              if (!interior) pr = (key0 + jj < L) ? pr : 0.f;
-              pd[jj] = pr * ks;
-              ds[jj] = pr * fmaf(__uint_as_float(dacc[jj]), ks, -delta);
-            }
+            const uint32_t hsh = drop_hash(e0 + jp, p.seed_lo, p.seed_hi);
+            const float k0 = ((hsh & 0xffffu) >= p.thr16) ? p.drop_scale : 0.f;
+            const float k1 = ((hsh >> 16) >= p.thr16) ? p.drop_scale : 0.f;
+            ds[2 * jp] = pd[2 * jp] * fmaf(__uint_as_float(dacc[2 * jp]), k0, -delta);
+            ds[2 * jp + 1] = pd[2 * jp + 1] * fmaf(__uint_as_float(dacc[2 * jp + 1]), k1, -delta);
+            pd[2 * jp] *= k0;
+            pd[2 * jp + 1] *= k1;
           }
         } else {
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            float pr = ex2(fmaf(__uint_as_float(sacc[jj]), p.scale_log2, -lse2));
-            if (!interior) pr = (key0 + jj < L) ? pr : 0.f;
-            pd[jj] = pr;
-            ds[jj] = pr * (__uint_as_float(dacc[jj]) - delta);
-          }
+          for (int jj = 0; jj < 32; ++jj) ds[jj] = pd[jj] * (__uint_as_float(dacc[jj]) - delta);
         }
       }
 #pragma unroll
@@ -450,6 +478,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     // tensor pipe while this block's P / dS are written out and its dV / dK / dQ MMAs are queued.
     tc_fence_before();
     __syncthreads();
+    TRACE_MARK();  // softmax / dS math
     if (threadIdx.x == 0 && n + 1 < nblocks) issue_s_dp((n + 1) % NT, (n + 1) / NT);
     // the previous block's dV/dK/dQ MMAs still read sP / sdS: wait before overwriting them
     if (g_pending) {
@@ -533,6 +562,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  TRACE_MARK();
+  TRACE_DUMP("bwd");
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 

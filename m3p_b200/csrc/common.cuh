@@ -53,12 +53,12 @@ int reduce_partials(const float* partial, int parts, int seg, float* const* outs
 // of the tensor the mask applies to, taken modulo 2^32.  tests/emu_ops.py restates this in torch.
 __host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t pair_idx, uint32_t seed_lo,
                                                        uint32_t seed_hi) {
+  // two multiply / xor-shift rounds (7 integer instructions per element PAIR): plenty for a Bernoulli
+  // mask over sequential indices, and cheap enough to regenerate in every backward kernel
   uint32_t x = (pair_idx ^ seed_lo) * 0x9E3779B1u + seed_hi;
-  x ^= x >> 16;
+  x ^= x >> 15;
   x *= 0x85EBCA6Bu;
   x ^= x >> 13;
-  x *= 0xC2B2AE35u;
-  x ^= x >> 16;
   return x;
 }
 __host__ __device__ __forceinline__ uint32_t drop_thr16(float p) {
