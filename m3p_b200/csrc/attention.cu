@@ -82,10 +82,15 @@ __device__ __forceinline__ uint32_t attn_drop_base(int bh, int q, int key0) {
 // =================================================================================================
 constexpr uint32_t FWD_SMEM_TILES = 96 * 1024;  // sQ 16K | sK 32K | pad 16K | sV 32K ; sP aliases first 64K
 constexpr uint32_t FWD_SMEM_BYTES = FWD_SMEM_TILES + 2 * 2 * 128 * 4 + 64 + 1024;
-constexpr int FWD_THREADS = 256;
+constexpr int FWD_MATH_THREADS = 256;
+constexpr int FWD_THREADS = FWD_MATH_THREADS + 32;
+constexpr uint32_t NBF_MATH = 1, NBF_KBLOCK0 = 2;  // named barriers: math-only sync; P k-block kb ready = 2 + kb
 
-// 256 threads: two threads per query row, each owning every other 32-key chunk (even / odd), so four
-// warps per scheduler hide the exp / max dependency chains; row max and sum are exchanged through smem.
+// Warp roles (288 threads): warps 0-7 = softmax, two threads per query row, each owning every other
+// 32-key chunk (thread half h takes chunks 2*kb + h); warp 8 = control (TMA loads, MMA issue).  The
+// P V product is issued per 64-key block as soon as both threads of every row have written that block
+// of P, so it runs on the tensor pipe underneath the exponentials of the later blocks.  O accumulates
+// in the TMEM columns of the first 64 scores, which every thread has consumed before block 0 is ready.
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                 const AttnKernelParams p) {
@@ -108,22 +113,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   TRACE_MARK();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int w4 = warp & 3, half = warp >> 2;
+  const bool control = warp == 8;
   const int u = blockIdx.x;
   const int mt = u % p.MT;
   const int h = (u / p.MT) % p.H;
   const int b = u / (p.MT * p.H);
 
-  if (warp == 0 && elect_one()) {
-    prefetch_tmap(&tmap_q);
-    prefetch_tmap(&tmap_kv);
-    mbar_init(bar_qk, 1);
-    mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
+  if (control) {
+    if (elect_one()) {
+      prefetch_tmap(&tmap_q);
+      prefetch_tmap(&tmap_kv);
+      mbar_init(bar_qk, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_o, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
@@ -131,138 +137,153 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar_qk, 48 * 1024);
-    tma_load_3d(sQ, &tmap_q, bar_qk, h * ATT_DH, mt * 128, b);
-    tma_load_3d(sK, &tmap_kv, bar_qk, p.d + h * ATT_DH, 0, b);
-    mbar_arrive_expect_tx(bar_v, 32 * 1024);
-    tma_load_3d(sV, &tmap_kv, bar_v, 2 * p.d + h * ATT_DH, 0, b);
-    mbar_wait(bar_qk, 0);
-    tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16(128, p.n_kv, 0, 0);
-    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
-#pragma unroll
-    for (int k = 0; k < ATT_DH / 16; ++k)
-      umma_ss(tmem_base, make_smem_desc(qa + k * 32, 0, 1024), make_smem_desc(ka + k * 32, 0, 1024), idesc,
-              k > 0 ? 1u : 0u);
-    umma_commit(bar_s);
-  }
-  TRACE_MARK();  // setup + TMA issue (+ thread 0: wait Q,K and issue S MMA)
-  __syncwarp();
-  mbar_wait(bar_s, 0);
-  __syncwarp();
-  tc_fence_after();
-  TRACE_MARK();  // S ready
-
-  // ---- softmax ----
-  // Interior 32-key chunks (entirely below the key length L) take a path without per-element masking;
-  // only the chunk that straddles L pays for the compares.  The dropout scale 1/(1-p) is folded into
-  // the final 1/sum normalisation, so a dropped weight is a plain select-to-zero.
-  const int row = w4 * 32 + lane;
-  const int q_idx = mt * 128 + row;
-  int L = p.seqlen[b];
-  L = L < 0 ? 0 : (L > p.S ? p.S : L);
-  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
   const int nchunk = (p.n_kv + 31) >> 5;
-  const int nfull = L >> 5;  // chunks with every key valid
-  float mx0 = -INFINITY, mx1 = -INFINITY;
-  for (int c = half; c < nchunk; c += 2) {
-    if (c * 32 >= L) break;
-    uint32_t acc[32];
-    tmem_ld_32x32b_x32(t_row + c * 32, acc);
-    tmem_ld_wait();
-    if (c < nfull) {
+  const int nkb = (p.n_kv + 63) >> 6;  // 64-key blocks of P / V
+
+  if (control) {
+    // ================================ control warp ================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_qk, 48 * 1024);
+      tma_load_3d(sQ, &tmap_q, bar_qk, h * ATT_DH, mt * 128, b);
+      tma_load_3d(sK, &tmap_kv, bar_qk, p.d + h * ATT_DH, 0, b);
+      mbar_arrive_expect_tx(bar_v, 32 * 1024);
+      tma_load_3d(sV, &tmap_kv, bar_v, 2 * p.d + h * ATT_DH, 0, b);
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, p.n_kv, 0, 0);
+      const uint64_t qd = make_smem_desc(smem_u32(sQ), 0, 1024), kd = make_smem_desc(smem_u32(sK), 0, 1024);
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        mx0 = fmaxf(mx0, __uint_as_float(acc[j]));
-        mx1 = fmaxf(mx1, __uint_as_float(acc[j + 1]));
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c * 32 + j < L) mx0 = fmaxf(mx0, __uint_as_float(acc[j]));
+      for (int k = 0; k < ATT_DH / 16; ++k) umma_ss(tmem_base, qd + k * 2, kd + k * 2, idesc, k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+      mbar_wait(bar_v, 0);
     }
-  }
-  s_max[half * 128 + row] = fmaxf(mx0, mx1);
-  __syncthreads();
-  TRACE_MARK();  // pass 1 (max)
-  const float mx = fmaxf(s_max[row], s_max[128 + row]);
-  const float mxs = (L > 0) ? mx * p.scale_log2 : 0.f;
-  float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-  const int bh = b * p.H + h;
-  for (int c = half; c < nchunk; c += 2) {
-    float pv[32];
-    if (c * 32 < L) {
+    __syncwarp();
+    const uint32_t idesc_pv = make_idesc_bf16(128, ATT_DH, 0, 1);
+    const uint64_t pd0 = make_smem_desc(smem_u32(sP), 0, 1024), vd0 = make_smem_desc(smem_u32(sV), 256 * 128, 1024);
+    const int nk = p.n_kv >> 4;
+    for (int kb = 0; kb < nkb; ++kb) {
+      named_bar_sync(NBF_KBLOCK0 + kb, FWD_THREADS);  // P[:, kb*64 .. +64) is in shared memory
+      if (lane == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int kk = kb * 4 + k4;
+          if (kk < nk)
+            umma_ss(tmem_base, pd0 + static_cast<uint64_t>(kb) * (TILE16K >> 4) + k4 * 2,
+                    vd0 + static_cast<uint64_t>(kk) * (2048 >> 4), idesc_pv, kk > 0 ? 1u : 0u);
+        }
+        if (kb == nkb - 1) umma_commit(bar_o);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================ softmax warps ================================
+    const int w4 = warp & 3, half = warp >> 2;
+    const int row = w4 * 32 + lane;
+    const int q_idx = mt * 128 + row;
+    int L = p.seqlen[b];
+    L = L < 0 ? 0 : (L > p.S ? p.S : L);
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
+    const int nfull = L >> 5;  // chunks with every key valid
+    TRACE_MARK();  // setup
+    mbar_wait(bar_s, 0);
+    __syncwarp();
+    tc_fence_after();
+    TRACE_MARK();  // S ready
+
+    // Interior 32-key chunks (entirely below the key length L) take a path without per-element masking;
+    // only the chunk that straddles L pays for the compares.  The dropout scale 1/(1-p) is folded into
+    // the final 1/sum normalisation, so a dropped weight is a plain select-to-zero.
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+    for (int c = half; c < nchunk; c += 2) {
+      if (c * 32 >= L) break;
       uint32_t acc[32];
       tmem_ld_32x32b_x32(t_row + c * 32, acc);
       tmem_ld_wait();
       if (c < nfull) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          pv[j + 0] = ex2(fmaf(__uint_as_float(acc[j + 0]), p.scale_log2, -mxs));
-          pv[j + 1] = ex2(fmaf(__uint_as_float(acc[j + 1]), p.scale_log2, -mxs));
-          pv[j + 2] = ex2(fmaf(__uint_as_float(acc[j + 2]), p.scale_log2, -mxs));
-          pv[j + 3] = ex2(fmaf(__uint_as_float(acc[j + 3]), p.scale_log2, -mxs));
-          sum0 += pv[j + 0]; sum1 += pv[j + 1]; sum2 += pv[j + 2]; sum3 += pv[j + 3];
+        for (int j = 0; j < 32; j += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(acc[j]));
+          mx1 = fmaxf(mx1, __uint_as_float(acc[j + 1]));
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float e = ex2(fmaf(__uint_as_float(acc[j]), p.scale_log2, -mxs));
-          pv[j] = (c * 32 + j < L) ? e : 0.f;
-          sum0 += pv[j];
-        }
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < L) mx0 = fmaxf(mx0, __uint_as_float(acc[j]));
       }
-      if (p.thr16 != 0) {
-        const uint32_t e0 = attn_drop_base(bh, q_idx, c * 32);
+    }
+    s_max[half * 128 + row] = fmaxf(mx0, mx1);
+    named_bar_sync(NBF_MATH, FWD_MATH_THREADS);
+    TRACE_MARK();  // pass 1 (max)
+    const float mx = fmaxf(s_max[row], s_max[128 + row]);
+    const float mxs = (L > 0) ? mx * p.scale_log2 : 0.f;
+    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+    const int bh = b * p.H + h;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int c = 2 * kb + half;
+      if (c < nchunk) {
+        float pv[32];
+        if (c * 32 < L) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(t_row + c * 32, acc);
+          tmem_ld_wait();
+          if (c < nfull) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t hsh = drop_hash((e0 >> 1) + j, p.seed_lo, p.seed_hi);
-          pv[2 * j] = ((hsh & 0xffffu) >= p.thr16) ? pv[2 * j] : 0.f;
-          pv[2 * j + 1] = ((hsh >> 16) >= p.thr16) ? pv[2 * j + 1] : 0.f;
+            for (int j = 0; j < 32; j += 4) {
+              pv[j + 0] = ex2(fmaf(__uint_as_float(acc[j + 0]), p.scale_log2, -mxs));
+              pv[j + 1] = ex2(fmaf(__uint_as_float(acc[j + 1]), p.scale_log2, -mxs));
+              pv[j + 2] = ex2(fmaf(__uint_as_float(acc[j + 2]), p.scale_log2, -mxs));
+              pv[j + 3] = ex2(fmaf(__uint_as_float(acc[j + 3]), p.scale_log2, -mxs));
+              sum0 += pv[j + 0]; sum1 += pv[j + 1]; sum2 += pv[j + 2]; sum3 += pv[j + 3];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float e = ex2(fmaf(__uint_as_float(acc[j]), p.scale_log2, -mxs));
+              pv[j] = (c * 32 + j < L) ? e : 0.f;
+              sum0 += pv[j];
+            }
+          }
+          if (p.thr16 != 0) {
+            const uint32_t e0 = attn_drop_base(bh, q_idx, c * 32) >> 1;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t hsh = drop_hash(e0 + j, p.seed_lo, p.seed_hi);
+              pv[2 * j] = ((hsh & 0xffffu) >= p.thr16) ? pv[2 * j] : 0.f;
+              pv[2 * j + 1] = ((hsh >> 16) >= p.thr16) ? pv[2 * j + 1] : 0.f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pv[j] = 0.f;
         }
+        // keys [c*32, c*32+32) live in k-block c/2, 16-byte chunks (c&1)*4 .. +3 of this row
+        uint8_t* blk = sP + kb * TILE16K;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 v = make_uint4(pack_bf16x2(pv[8 * g + 0], pv[8 * g + 1]), pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]),
+                                     pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]), pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]));
+          *reinterpret_cast<uint4*>(blk + swz_off(row, (c & 1) * 4 + g)) = v;
+        }
+        fence_proxy_async_smem();
+      } else {
+        // n_kv ends inside this block's first 32 keys: the other half of the block must read as zeros
+        uint8_t* blk = sP + kb * TILE16K;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(blk + swz_off(row, (c & 1) * 4 + g)) = make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) pv[j] = 0.f;
+      tc_fence_before();
+      named_bar_arrive(NBF_KBLOCK0 + kb, FWD_THREADS);
     }
-    // keys [c*32, c*32+32) live in k-block c/2, 16-byte chunks (c&1)*4 .. +3 of this row
-    uint8_t* blk = sP + (c >> 1) * TILE16K;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const uint4 v = make_uint4(pack_bf16x2(pv[8 * g + 0], pv[8 * g + 1]), pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]),
-                                 pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]), pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]));
-      *reinterpret_cast<uint4*>(blk + swz_off(row, (c & 1) * 4 + g)) = v;
-    }
-  }
-  s_sum[half * 128 + row] = (sum0 + sum1) + (sum2 + sum3);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  TRACE_MARK();  // pass 2 (exp, P -> smem)
-
-  if (threadIdx.x == 0) {
+    s_sum[half * 128 + row] = (sum0 + sum1) + (sum2 + sum3);
+    named_bar_sync(NBF_MATH, FWD_MATH_THREADS);
+    TRACE_MARK();  // pass 2 (exp, P -> smem)
+    const float sum = s_sum[row] + s_sum[128 + row];
+    mbar_wait(bar_o, 0);
+    __syncwarp();
     tc_fence_after();
-    mbar_wait(bar_v, 0);
-    const uint32_t idesc = make_idesc_bf16(128, ATT_DH, 0, 1);
-    const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
-    const int nk = p.n_kv >> 4;
-    for (int kk = 0; kk < nk; ++kk) {
-      const uint64_t adesc = make_smem_desc(pa + (kk >> 2) * TILE16K + (kk & 3) * 32, 0, 1024);
-      const uint64_t bdesc = make_smem_desc(va + kk * 2048, 256 * 128, 1024);
-      umma_ss(tmem_base, adesc, bdesc, idesc, kk > 0 ? 1u : 0u);
-    }
-    umma_commit(bar_o);
-  }
-  const float sum = s_sum[row] + s_sum[128 + row];
-  __syncwarp();
-  mbar_wait(bar_o, 0);
-  __syncwarp();
-  tc_fence_after();
-  TRACE_MARK();  // PV MMA done
-
-  {
+    TRACE_MARK();  // PV MMA done
     const float inv = sum > 0.f ? p.drop_scale / sum : 0.f;  // dropout's 1/(1-p) folded in here
     uint32_t o0[32];
     tmem_ld_32x32b_x32(t_row + half * 32, o0);  // this thread's 32 of the 64 output columns
@@ -283,7 +304,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   TRACE_MARK();  // epilogue
   TRACE_DUMP("fwd");
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (control) tmem_dealloc(tmem_base, 256);
 }
 
 // =================================================================================================
@@ -304,7 +325,19 @@ __device__ __forceinline__ void store_acc32(__nv_bfloat16* dst, const uint32_t* 
                        pack_bf16x2(__uint_as_float(acc[8 * g + 6]) * mul, __uint_as_float(acc[8 * g + 7]) * mul));
 }
 
-__global__ void __launch_bounds__(256, 1)
+// Warp roles (288 threads): warps 0-7 do the softmax / dS math and the epilogues (two threads per
+// query row, 64 keys each); warp 8 is the control warp — one lane issues every TMA load and every
+// tcgen05.mma, so the math warps never stall behind MMA issue and the tensor pipe works on block n's
+// dV / dK / dQ while the math warps are already on block n+1.  Hand-offs:
+//   bar_sd (mbarrier, tcgen05.commit)  control -> math : S and dP of the block are in TMEM
+//   named barrier 1 (math arrive, control sync)        : S / dP have been read out of TMEM
+//   named barrier 2 (math arrive, control sync)        : P / dS of the block are in shared memory
+//   bar_g  (mbarrier, tcgen05.commit)  control -> math : the block's dV / dK / dQ MMAs have retired
+constexpr int BWD_MATH_THREADS = 256;
+constexpr int BWD_THREADS = BWD_MATH_THREADS + 32;
+constexpr uint32_t NB_TMEM_FREE = 1, NB_SMEM_READY = 2, NB_MATH = 3;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_o, const AttnKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -330,17 +363,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   const int h = blockIdx.x % p.H;
   const int b = blockIdx.x / p.H;
   const int bh = blockIdx.x;
+  const bool control = warp == 8;
 
-  if (warp == 0 && elect_one()) {
-    prefetch_tmap(&tmap_qkv);
-    prefetch_tmap(&tmap_do);
-    prefetch_tmap(&tmap_o);
-    mbar_init(bar_ld, 1);
-    mbar_init(bar_sd, 1);
-    mbar_init(bar_g, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
+  if (control) {
+    if (elect_one()) {
+      prefetch_tmap(&tmap_qkv);
+      prefetch_tmap(&tmap_do);
+      prefetch_tmap(&tmap_o);
+      mbar_init(bar_ld, 1);
+      mbar_init(bar_sd, 1);
+      mbar_init(bar_g, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -349,222 +384,230 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (threadIdx.x == 0) {
-    // Q, K, V, dO and (temporarily, in the P staging buffer) the forward output O
-    mbar_arrive_expect_tx(bar_ld, 5 * 32 * 1024);
-    tma_load_3d(sQ, &tmap_qkv, bar_ld, h * ATT_DH, 0, b);
-    tma_load_3d(sK, &tmap_qkv, bar_ld, p.d + h * ATT_DH, 0, b);
-    tma_load_3d(sV, &tmap_qkv, bar_ld, 2 * p.d + h * ATT_DH, 0, b);
-    tma_load_3d(sdO, &tmap_do, bar_ld, h * ATT_DH, 0, b);
-    tma_load_3d(sP, &tmap_o, bar_ld, h * ATT_DH, 0, b);
-  }
-  {
-    const int r = threadIdx.x;
-    s_lse[r] = (r < p.S) ? p.lse[static_cast<long long>(bh) * p.S + r] : INFINITY;  // phantom rows: exp2(-inf) = 0
-  }
-  TRACE_MARK();  // setup
-  __syncwarp();
-  mbar_wait(bar_ld, 0);
-  __syncwarp();
-  TRACE_MARK();  // loads landed
-
+  const int NT = p.MT;
+  const int nblocks = NT * NT;
   int L = p.seqlen[b];
   L = L < 0 ? 0 : (L > p.S ? p.S : L);
-  const int NT = p.MT;
-  const int w4 = warp & 3, half = warp >> 2;
-  const int row = w4 * 32 + lane;
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
-  const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // S, dP : K-major A and B
-  const uint32_t idesc_t = make_idesc_bf16(128, ATT_DH, 1, 1);  // dV, dK: MN-major A and B
-  const uint32_t idesc_q = make_idesc_bf16(128, ATT_DH, 0, 1);  // dQ    : K-major A, MN-major B
-  uint32_t ph_sd = 0, ph_g = 0;
-  int g_pending = 0;
 
-  // S = Q_i K_j^T and dP = dO_i V_j^T for block (i, j) into TMEM; one thread issues.
-  auto issue_s_dp = [&](int i, int j) {
-    tc_fence_after();
-    const uint32_t qa = smem_u32(sQ) + i * TILE16K, ka = smem_u32(sK) + j * TILE16K;
-    const uint32_t da = smem_u32(sdO) + i * TILE16K, va = smem_u32(sV) + j * TILE16K;
+  if (control) {
+    // ================================ control warp ================================
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);     // S, dP : K-major A and B
+    const uint32_t idesc_t = make_idesc_bf16(128, ATT_DH, 1, 1);  // dV, dK: MN-major A and B
+    const uint32_t idesc_q = make_idesc_bf16(128, ATT_DH, 0, 1);  // dQ    : K-major A, MN-major B
+    // Descriptor bases (address field = tile 0): a tile / k-step offset is one 64-bit add of (bytes >> 4),
+    // so the issuing thread spends a few instructions per MMA instead of rebuilding both descriptors.
+    constexpr uint64_t T16 = TILE16K >> 4, KS = 2048 >> 4, K32 = 32 >> 4;
+    const uint64_t dQk = make_smem_desc(smem_u32(sQ), 0, 1024), dKk = make_smem_desc(smem_u32(sK), 0, 1024);
+    const uint64_t dVk = make_smem_desc(smem_u32(sV), 0, 1024), dOk = make_smem_desc(smem_u32(sdO), 0, 1024);
+    const uint64_t dSk = make_smem_desc(smem_u32(sdS), 0, 1024);                  // dS as K-major A (dQ)
+    const uint64_t dPm = make_smem_desc(smem_u32(sP), TILE16K, 1024);             // P^T  as MN-major A (dV)
+    const uint64_t dSm = make_smem_desc(smem_u32(sdS), TILE16K, 1024);            // dS^T as MN-major A (dK)
+    const uint64_t dOm = make_smem_desc(smem_u32(sdO), TILE16K, 1024);            // dO as MN-major B (dV)
+    const uint64_t dQm = make_smem_desc(smem_u32(sQ), TILE16K, 1024);             // Q  as MN-major B (dK)
+    const uint64_t dKm = make_smem_desc(smem_u32(sK), TILE16K, 1024);             // K  as MN-major B (dQ)
+    auto issue_s_dp = [&](int i, int j) {
+      tc_fence_after();
+      const uint64_t qa = dQk + i * T16, ka = dKk + j * T16, da = dOk + i * T16, va = dVk + j * T16;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_ss(tmem_base + TM_S, make_smem_desc(qa + k * 32, 0, 1024), make_smem_desc(ka + k * 32, 0, 1024), idesc_s,
-              k > 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) umma_ss(tmem_base + TM_S, qa + k * K32, ka + k * K32, idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_ss(tmem_base + TM_DP, make_smem_desc(da + k * 32, 0, 1024), make_smem_desc(va + k * 32, 0, 1024), idesc_s,
-              k > 0 ? 1u : 0u);
-    umma_commit(bar_sd);
-  };
-
-  if (threadIdx.x == 0) issue_s_dp(0, 0);  // runs on the tensor pipe while delta is computed below
-  // ---- delta = rowsum(dO * O) from the TMA-staged (128B-swizzled) tiles: one thread per query row ----
-  {
-    const int r = threadIdx.x;
-    const uint8_t* dob = sdO + (r >> 7) * TILE16K;
-    const uint8_t* ob = sP + (r >> 7) * TILE16K;
-    float dl0 = 0.f, dl1 = 0.f;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const uint32_t off = swz_off(r & 127, g);
-      const uint4 a = *reinterpret_cast<const uint4*>(dob + off);
-      const uint4 o = *reinterpret_cast<const uint4*>(ob + off);
-      dl0 = fmaf(bf16_lo(a.x), bf16_lo(o.x), dl0); dl1 = fmaf(bf16_hi(a.x), bf16_hi(o.x), dl1);
-      dl0 = fmaf(bf16_lo(a.y), bf16_lo(o.y), dl0); dl1 = fmaf(bf16_hi(a.y), bf16_hi(o.y), dl1);
-      dl0 = fmaf(bf16_lo(a.z), bf16_lo(o.z), dl0); dl1 = fmaf(bf16_hi(a.z), bf16_hi(o.z), dl1);
-      dl0 = fmaf(bf16_lo(a.w), bf16_lo(o.w), dl0); dl1 = fmaf(bf16_hi(a.w), bf16_hi(o.w), dl1);
+      for (int k = 0; k < 4; ++k) umma_ss(tmem_base + TM_DP, da + k * K32, va + k * K32, idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(bar_sd);
+    };
+    if (lane == 0) {
+      // Q, K, V, dO and (temporarily, in the P staging buffer) the forward output O
+      mbar_arrive_expect_tx(bar_ld, 5 * 32 * 1024);
+      tma_load_3d(sQ, &tmap_qkv, bar_ld, h * ATT_DH, 0, b);
+      tma_load_3d(sK, &tmap_qkv, bar_ld, p.d + h * ATT_DH, 0, b);
+      tma_load_3d(sV, &tmap_qkv, bar_ld, 2 * p.d + h * ATT_DH, 0, b);
+      tma_load_3d(sdO, &tmap_do, bar_ld, h * ATT_DH, 0, b);
+      tma_load_3d(sP, &tmap_o, bar_ld, h * ATT_DH, 0, b);
+      mbar_wait(bar_ld, 0);
+      issue_s_dp(0, 0);
     }
-    s_delta[r] = dl0 + dl1;
-  }
-  __syncthreads();  // s_delta / s_lse visible; O has been consumed before the first P tile overwrites it
-  TRACE_MARK();  // delta
-  const int nblocks = NT * NT;
-  for (int n = 0; n < nblocks; ++n) {
-    const int j = n / NT, i = n % NT;
     __syncwarp();
-    mbar_wait(bar_sd, ph_sd);
-    ph_sd ^= 1;
-    __syncwarp();
-    tc_fence_after();
-    TRACE_MARK();  // S, dP ready
-
-    // ---- P and dS for this thread's row x 64 keys, kept packed in registers ----
-    const int q = i * 128 + row;
-    const float lse2 = s_lse[q], delta = s_delta[q];
-    uint32_t ppk[2][16], dpk[2][16];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int col0 = half * 64 + c * 32;  // column inside the 128-key tile
-      const int key0 = j * 128 + col0;
-      uint32_t sacc[32], dacc[32];
-      tmem_ld_32x32b_x32(t_lane + TM_S + col0, sacc);
-      tmem_ld_32x32b_x32(t_lane + TM_DP + col0, dacc);
-      tmem_ld_wait();
-      float pd[32], ds[32];
-      if (key0 >= L) {
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) { pd[jj] = 0.f; ds[jj] = 0.f; }
-      } else {
-        // P (normalised: the forward's log2-sum-exp is subtracted inside the exponent)
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) pd[jj] = ex2(fmaf(__uint_as_float(sacc[jj]), p.scale_log2, -lse2));
-        if (key0 + 32 > L) {  // the one chunk that straddles the key length
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) pd[jj] = (key0 + jj < L) ? pd[jj] : 0.f;
-        }
-        if (p.thr16 != 0) {
-          const uint32_t e0 = attn_drop_base(bh, q, key0) >> 1;
-#pragma unroll
-          for (int jp = 0; jp < 16; ++jp) {
-            const uint32_t hsh = drop_hash(e0 + jp, p.seed_lo, p.seed_hi);
-            const float k0 = ((hsh & 0xffffu) >= p.thr16) ? p.drop_scale : 0.f;
-            const float k1 = ((hsh >> 16) >= p.thr16) ? p.drop_scale : 0.f;
-            ds[2 * jp] = pd[2 * jp] * fmaf(__uint_as_float(dacc[2 * jp]), k0, -delta);
-            ds[2 * jp + 1] = pd[2 * jp + 1] * fmaf(__uint_as_float(dacc[2 * jp + 1]), k1, -delta);
-            pd[2 * jp] *= k0;
-            pd[2 * jp + 1] *= k1;
-          }
-        } else {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) ds[jj] = pd[jj] * (__uint_as_float(dacc[jj]) - delta);
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < 16; ++g) {
-        ppk[c][g] = pack_bf16x2(pd[2 * g], pd[2 * g + 1]);
-        dpk[c][g] = pack_bf16x2(ds[2 * g], ds[2 * g + 1]);
-      }
-    }
-    // S / dP are in registers: TMEM is free for the next block's score MMAs, which then run on the
-    // tensor pipe while this block's P / dS are written out and its dV / dK / dQ MMAs are queued.
-    tc_fence_before();
-    __syncthreads();
-    TRACE_MARK();  // softmax / dS math
-    if (threadIdx.x == 0 && n + 1 < nblocks) issue_s_dp((n + 1) % NT, (n + 1) / NT);
-    // the previous block's dV/dK/dQ MMAs still read sP / sdS: wait before overwriting them
-    if (g_pending) {
+    for (int n = 0; n < nblocks; ++n) {
+      const int j = n / NT, i = n % NT;
+      named_bar_sync(NB_TMEM_FREE, BWD_THREADS);
+      if (lane == 0 && n + 1 < nblocks) issue_s_dp((n + 1) % NT, (n + 1) / NT);
       __syncwarp();
-      mbar_wait(bar_g, ph_g);
-      ph_g ^= 1;
-      g_pending = 0;
+      named_bar_sync(NB_SMEM_READY, BWD_THREADS);
+      if (lane == 0) {
+        tc_fence_after();
+        const uint64_t doa = dOm + i * T16, qa = dQm + i * T16, ka = dKm + j * T16;
+        const uint32_t acc_kv = i > 0 ? 1u : 0u, acc_q = j > 0 ? 1u : 0u;
+        // dV_j += Pd^T dO_i ; dK_j += dS^T Q_i      (M = 128 keys, N = 64, K = 128 queries)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_ss(tmem_base + TM_DV, dPm + k * KS, doa + k * KS, idesc_t, k > 0 ? 1u : acc_kv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_ss(tmem_base + TM_DK, dSm + k * KS, qa + k * KS, idesc_t, k > 0 ? 1u : acc_kv);
+        // dQ_i += dS K_j                             (M = 128 queries, N = 64, K = 128 keys)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tmem_base + TM_DQ + i * ATT_DH, dSk + (k >> 2) * T16 + (k & 3) * K32, ka + k * KS, idesc_q,
+                  k > 0 ? 1u : acc_q);
+        umma_commit(bar_g);
+      }
       __syncwarp();
     }
+  } else {
+    // ================================ math warps ================================
+    const int w4 = warp & 3, half = warp >> 2;
+    const int row = w4 * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
     {
-      uint8_t* pblk = sP + half * TILE16K;
-      uint8_t* dblk = sdS + half * TILE16K;
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t off = swz_off(row, c * 4 + g);
-          *reinterpret_cast<uint4*>(pblk + off) = make_uint4(ppk[c][4 * g], ppk[c][4 * g + 1], ppk[c][4 * g + 2], ppk[c][4 * g + 3]);
-          *reinterpret_cast<uint4*>(dblk + off) = make_uint4(dpk[c][4 * g], dpk[c][4 * g + 1], dpk[c][4 * g + 2], dpk[c][4 * g + 3]);
-        }
+      const int r = threadIdx.x;
+      s_lse[r] = (r < p.S) ? p.lse[static_cast<long long>(bh) * p.S + r] : INFINITY;  // phantom rows: exp2(-inf) = 0
     }
-    fence_proxy_async_smem();
-    __syncthreads();
-
-    if (threadIdx.x == 0) {
-      tc_fence_after();
-      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS);
-      const uint32_t doa = smem_u32(sdO) + i * TILE16K, qa = smem_u32(sQ) + i * TILE16K;
-      const uint32_t ka = smem_u32(sK) + j * TILE16K;
-      // dV_j += Pd^T dO_i ; dK_j += dS^T Q_i      (M = 128 keys, N = 64, K = 128 queries)
+    TRACE_MARK();  // setup
+    mbar_wait(bar_ld, 0);
+    __syncwarp();
+    TRACE_MARK();  // loads landed
+    // ---- delta = rowsum(dO * O) from the TMA-staged (128B-swizzled) tiles: one thread per query row ----
+    {
+      const int r = threadIdx.x;
+      const uint8_t* dob = sdO + (r >> 7) * TILE16K;
+      const uint8_t* ob = sP + (r >> 7) * TILE16K;
+      float dl0 = 0.f, dl1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_ss(tmem_base + TM_DV, make_smem_desc(pa + k * 2048, TILE16K, 1024),
-                make_smem_desc(doa + k * 2048, TILE16K, 1024), idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_ss(tmem_base + TM_DK, make_smem_desc(sa + k * 2048, TILE16K, 1024),
-                make_smem_desc(qa + k * 2048, TILE16K, 1024), idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-      // dQ_i += dS K_j                             (M = 128 queries, N = 64, K = 128 keys)
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_ss(tmem_base + TM_DQ + i * ATT_DH, make_smem_desc(sa + (k >> 2) * TILE16K + (k & 3) * 32, 0, 1024),
-                make_smem_desc(ka + k * 2048, TILE16K, 1024), idesc_q, (j > 0 || k > 0) ? 1u : 0u);
-      umma_commit(bar_g);
-    }
-    g_pending = 1;
-
-    if (i == NT - 1) {
-      // ---- dK_j, dV_j complete: TMEM -> bf16 -> dqkv (the softmax scale is applied here, not per element) ----
-      __syncwarp();
-      mbar_wait(bar_g, ph_g);
-      ph_g ^= 1;
-      g_pending = 0;
-      __syncwarp();
-      tc_fence_after();
-      uint32_t a[32], v[32];
-      tmem_ld_32x32b_x32(t_lane + TM_DK + half * 32, a);
-      tmem_ld_32x32b_x32(t_lane + TM_DV + half * 32, v);
-      tmem_ld_wait();
-      const int key = j * 128 + row;
-      if (key < p.S) {
-        __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.S + key) * (3 * p.d) + h * ATT_DH + half * 32;
-        store_acc32(base + p.d, a, p.scale);
-        store_acc32(base + 2 * p.d, v, 1.0f);
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t off = swz_off(r & 127, g);
+        const uint4 a = *reinterpret_cast<const uint4*>(dob + off);
+        const uint4 o = *reinterpret_cast<const uint4*>(ob + off);
+        dl0 = fmaf(bf16_lo(a.x), bf16_lo(o.x), dl0); dl1 = fmaf(bf16_hi(a.x), bf16_hi(o.x), dl1);
+        dl0 = fmaf(bf16_lo(a.y), bf16_lo(o.y), dl0); dl1 = fmaf(bf16_hi(a.y), bf16_hi(o.y), dl1);
+        dl0 = fmaf(bf16_lo(a.z), bf16_lo(o.z), dl0); dl1 = fmaf(bf16_hi(a.z), bf16_hi(o.z), dl1);
+        dl0 = fmaf(bf16_lo(a.w), bf16_lo(o.w), dl0); dl1 = fmaf(bf16_hi(a.w), bf16_hi(o.w), dl1);
       }
-      tc_fence_before();  // ordered before the next block's barriers, which precede the MMAs that reuse dK / dV
+      s_delta[r] = dl0 + dl1;
     }
-  }
-  __syncthreads();
-  // ---- dQ ----
-  tc_fence_after();
-  for (int i = 0; i < NT; ++i) {
-    uint32_t a[32];
-    tmem_ld_32x32b_x32(t_lane + TM_DQ + i * ATT_DH + half * 32, a);
-    tmem_ld_wait();
-    const int q = i * 128 + row;
-    if (q < p.S) {
-      __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.S + q) * (3 * p.d) + h * ATT_DH + half * 32;
-      store_acc32(base, a, p.scale);
+    named_bar_sync(NB_MATH, BWD_MATH_THREADS);  // s_delta / s_lse visible; O consumed before P overwrites it
+    TRACE_MARK();  // delta
+    uint32_t ph_sd = 0, ph_g = 0;
+    int g_pending = 0;
+    for (int n = 0; n < nblocks; ++n) {
+      const int j = n / NT, i = n % NT;
+      mbar_wait(bar_sd, ph_sd);
+      ph_sd ^= 1;
+      __syncwarp();
+      tc_fence_after();
+      TRACE_MARK();  // S, dP ready
+
+      // ---- P and dS for this thread's row x 64 keys, kept packed in registers ----
+      const int q = i * 128 + row;
+      const float lse2 = s_lse[q], delta = s_delta[q];
+      uint32_t ppk[2][16], dpk[2][16];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = half * 64 + c * 32;  // column inside the 128-key tile
+        const int key0 = j * 128 + col0;
+        uint32_t sacc[32], dacc[32];
+        tmem_ld_32x32b_x32(t_lane + TM_S + col0, sacc);
+        tmem_ld_32x32b_x32(t_lane + TM_DP + col0, dacc);
+        tmem_ld_wait();
+        if (c == 1) {
+          // everything this thread needs from S / dP is in registers: the control warp may start the
+          // next block's score MMAs while this chunk's math runs
+          tc_fence_before();
+          named_bar_arrive(NB_TMEM_FREE, BWD_THREADS);
+        }
+        float pd[32], ds[32];
+        if (key0 >= L) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) { pd[jj] = 0.f; ds[jj] = 0.f; }
+        } else {
+          // P (normalised: the forward's log2-sum-exp is subtracted inside the exponent)
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) pd[jj] = ex2(fmaf(__uint_as_float(sacc[jj]), p.scale_log2, -lse2));
+          if (key0 + 32 > L) {  // the one chunk that straddles the key length
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) pd[jj] = (key0 + jj < L) ? pd[jj] : 0.f;
+          }
+          if (p.thr16 != 0) {
+            const uint32_t e0 = attn_drop_base(bh, q, key0) >> 1;
+#pragma unroll
+            for (int jp = 0; jp < 16; ++jp) {
+              const uint32_t hsh = drop_hash(e0 + jp, p.seed_lo, p.seed_hi);
+              const float k0 = ((hsh & 0xffffu) >= p.thr16) ? p.drop_scale : 0.f;
+              const float k1 = ((hsh >> 16) >= p.thr16) ? p.drop_scale : 0.f;
+              ds[2 * jp] = pd[2 * jp] * fmaf(__uint_as_float(dacc[2 * jp]), k0, -delta);
+              ds[2 * jp + 1] = pd[2 * jp + 1] * fmaf(__uint_as_float(dacc[2 * jp + 1]), k1, -delta);
+              pd[2 * jp] *= k0;
+              pd[2 * jp + 1] *= k1;
+            }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) ds[jj] = pd[jj] * (__uint_as_float(dacc[jj]) - delta);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          ppk[c][g] = pack_bf16x2(pd[2 * g], pd[2 * g + 1]);
+          dpk[c][g] = pack_bf16x2(ds[2 * g], ds[2 * g + 1]);
+        }
+      }
+      TRACE_MARK();  // softmax / dS math
+      // the previous block's dV/dK/dQ MMAs still read sP / sdS: wait before overwriting them
+      if (g_pending) {
+        mbar_wait(bar_g, ph_g);
+        ph_g ^= 1;
+        g_pending = 0;
+        __syncwarp();
+      }
+      {
+        uint8_t* pblk = sP + half * TILE16K;
+        uint8_t* dblk = sdS + half * TILE16K;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t off = swz_off(row, c * 4 + g);
+            *reinterpret_cast<uint4*>(pblk + off) = make_uint4(ppk[c][4 * g], ppk[c][4 * g + 1], ppk[c][4 * g + 2], ppk[c][4 * g + 3]);
+            *reinterpret_cast<uint4*>(dblk + off) = make_uint4(dpk[c][4 * g], dpk[c][4 * g + 1], dpk[c][4 * g + 2], dpk[c][4 * g + 3]);
+          }
+      }
+      fence_proxy_async_smem();
+      named_bar_arrive(NB_SMEM_READY, BWD_THREADS);
+      g_pending = 1;
+
+      if (i == NT - 1) {
+        // ---- dK_j, dV_j complete: TMEM -> bf16 -> dqkv (the softmax scale is applied here, not per element) ----
+        mbar_wait(bar_g, ph_g);
+        ph_g ^= 1;
+        g_pending = 0;
+        __syncwarp();
+        tc_fence_after();
+        uint32_t a[32], v[32];
+        tmem_ld_32x32b_x32(t_lane + TM_DK + half * 32, a);
+        tmem_ld_32x32b_x32(t_lane + TM_DV + half * 32, v);
+        tmem_ld_wait();
+        const int key = j * 128 + row;
+        if (key < p.S) {
+          __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.S + key) * (3 * p.d) + h * ATT_DH + half * 32;
+          store_acc32(base + p.d, a, p.scale);
+          store_acc32(base + 2 * p.d, v, 1.0f);
+        }
+        tc_fence_before();  // ordered before this thread's next named-barrier arrive, which precedes the MMAs that reuse dK / dV
+      }
+    }
+    // ---- dQ (the last block's bar_g wait above covers every MMA) ----
+    tc_fence_after();
+    for (int i = 0; i < NT; ++i) {
+      uint32_t a[32];
+      tmem_ld_32x32b_x32(t_lane + TM_DQ + i * ATT_DH + half * 32, a);
+      tmem_ld_wait();
+      const int q = i * 128 + row;
+      if (q < p.S) {
+        __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.S + q) * (3 * p.d) + h * ATT_DH + half * 32;
+        store_acc32(base, a, p.scale);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   TRACE_MARK();
   TRACE_DUMP("bwd");
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (control) tmem_dealloc(tmem_base, 512);
 }
 
 static int fill_params(const m3p_attn_args* a, AttnKernelParams& p, const char* who) {
@@ -637,7 +680,20 @@ extern "C" int m3p_attention_bwd(const m3p_attn_args* a, m3p_stream_t stream_) {
     M3P_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
     attr_set = true;
   }
-  attn_bwd_kernel<<<p.B * p.H, 256, BWD_SMEM_BYTES, stream>>>(tqkv, tdo, to, p);
+  attn_bwd_kernel<<<p.B * p.H, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(tqkv, tdo, to, p);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
+}
+
+// bring-up aid (not part of the public header): resident CTAs per SM of the attention kernels
+extern "C" __attribute__((visibility("default"))) int m3p_debug_attn_occupancy(int bwd) {
+  int n = -1;
+  if (bwd) {
+    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_bwd_kernel, BWD_THREADS, BWD_SMEM_BYTES);
+  } else {
+    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_fwd_kernel, FWD_THREADS, FWD_SMEM_BYTES);
+  }
+  return n;
 }

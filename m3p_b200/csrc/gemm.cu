@@ -338,6 +338,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
+      const uint64_t adesc_base = make_smem_desc(smem_u32(smem), p.a_lbo, p.a_sbo);
+      const uint64_t bdesc_base = make_smem_desc(smem_u32(smem) + Cfg::A_BYTES, p.b_lbo, p.b_sbo);
+      const uint64_t a_kstep4 = p.a_kstep >> 4, b_kstep4 = p.b_kstep >> 4;
       for (int u = unit0; u < p.num_units; u += unit_stride) {
         int m_tile, n_tile, ks;
         decode_unit(p, u, m_tile, n_tile, ks);
@@ -349,12 +352,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          // descriptors differ from the stage-0 / k-0 ones only in the (address >> 4) field: one 64-bit
+          // add per MMA instead of rebuilding them (the single issuing thread is latency-bound)
+          const uint64_t adesc0 = adesc_base + static_cast<uint64_t>((stage * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t bdesc0 = bdesc_base + static_cast<uint64_t>((stage * Cfg::STAGE_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc(a_addr + k * p.a_kstep, p.a_lbo, p.a_sbo);
-            const uint64_t bdesc = make_smem_desc(b_addr + k * p.b_kstep, p.b_lbo, p.b_sbo);
+            const uint64_t adesc = adesc0 + static_cast<uint64_t>(k) * a_kstep4;
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(k) * b_kstep4;
             if constexpr (CTA2) umma_ss_2sm(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_ss(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }

@@ -4,7 +4,8 @@ cp m3p_b200/libm3p_sm100.so /tmp/lib_prod.so
 M3P_NVCC_EXTRA=-DM3P_ATTN_TRACE python -m m3p_b200.build --force > /dev/null
 python - <<'PY'
 import torch
-from m3p_b200 import ops
+from m3p_b200 import ops, lib as L
+print('occupancy fwd', L.load().m3p_debug_attn_occupancy(0), 'bwd', L.load().m3p_debug_attn_occupancy(1))
 B,S,H=64,228,12; d=H*64
 qkv=(torch.randn(B*S,3*d,device='cuda')*0.7).bfloat16()
 seqlen=torch.full((B,),S,device='cuda',dtype=torch.int32)
