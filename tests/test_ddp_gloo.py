@@ -41,6 +41,44 @@ def _worker(rank, world, port, overlap, q):
     dist.destroy_process_group()
 
 
+def _worker_sparse(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from m3p_b200.ddp import GradReducer
+    m = _FakeModel(rank)
+    V, d = 50, 8
+    g = torch.Generator().manual_seed(100 + rank)
+    ids = torch.randint(0, V, (12,), generator=g)          # duplicates on purpose
+    rows = torch.randn(12, d, generator=g)
+    m._emb_grad = torch.zeros(V, d).index_add_(0, ids, rows)
+    m._proj_grad = m._emb_grad
+    m._emb_touched, m._emb_dense_dirty = [ids], False
+    dense = [torch.zeros(V, d) for _ in range(world)]
+    dist.all_gather(dense, m._emb_grad.clone())
+    want = sum(dense) / world
+    red = GradReducer(m)
+    red.finish()
+    ok = torch.allclose(m._emb_grad, want, atol=1e-6) and not m._emb_dense_dirty
+    # the ids every rank touched are remembered, so the next zero_grad can clear exactly those rows
+    cleared = m._emb_grad.clone().index_fill_(0, m._emb_touched[0], 0.0)
+    ok = ok and float(cleared.abs().max()) == 0.0
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_row_sparse_embedding_exchange_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sparse, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
