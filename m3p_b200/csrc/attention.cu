@@ -93,7 +93,7 @@ constexpr uint32_t NBF_MATH = 1, NBF_KBLOCK0 = 2;  // named barriers: math-only 
 // in the TMEM columns of the first 64 scores, which every thread has consumed before block 0 is ready.
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                const AttnKernelParams p) {
+                const __grid_constant__ CUtensorMap tmap_ctx, const AttnKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -288,16 +288,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint32_t o0[32];
     tmem_ld_32x32b_x32(t_row + half * 32, o0);  // this thread's 32 of the 64 output columns
     tmem_ld_wait();
-    if (q_idx < p.S) {
-      __nv_bfloat16* op = p.ctx + (static_cast<long long>(b) * p.S + q_idx) * p.d + h * ATT_DH + half * 32;
-      uint4* o4 = reinterpret_cast<uint4*>(op);
+    // O tile -> the (now dead) V staging area in the swizzled layout -> one TMA bulk store; rows >= S are clipped
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        o4[g] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * g + 0]) * inv, __uint_as_float(o0[8 * g + 1]) * inv),
-                           pack_bf16x2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
-                           pack_bf16x2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
-                           pack_bf16x2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv));
-      if (half == 0) p.lse[(static_cast<long long>(bh)) * p.S + q_idx] = (sum > 0.f) ? mxs + log2f(sum) : INFINITY;
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(sV + swz_off(row, half * 4 + g)) =
+          make_uint4(pack_bf16x2(__uint_as_float(o0[8 * g + 0]) * inv, __uint_as_float(o0[8 * g + 1]) * inv),
+                     pack_bf16x2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
+                     pack_bf16x2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
+                     pack_bf16x2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv));
+    if (half == 0 && q_idx < p.S)
+      p.lse[(static_cast<long long>(bh)) * p.S + q_idx] = (sum > 0.f) ? mxs + log2f(sum) : INFINITY;
+    fence_proxy_async_smem();
+    named_bar_sync(NBF_MATH, FWD_MATH_THREADS);
+    if (threadIdx.x == 0) {
+      tma_store_3d(&tmap_ctx, sV, h * ATT_DH, mt * 128, b);
+      tma_store_commit();
+      tma_store_wait<0>();  // shared memory must outlive the bulk store that reads it
     }
   }
   tc_fence_before();
@@ -339,7 +345,8 @@ constexpr uint32_t NB_TMEM_FREE = 1, NB_SMEM_READY = 2, NB_MATH = 3;
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                const __grid_constant__ CUtensorMap tmap_o, const AttnKernelParams p) {
+                const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_dqkv,
+                const AttnKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -370,6 +377,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       prefetch_tmap(&tmap_qkv);
       prefetch_tmap(&tmap_do);
       prefetch_tmap(&tmap_o);
+      prefetch_tmap(&tmap_dqkv);
       mbar_init(bar_ld, 1);
       mbar_init(bar_sd, 1);
       mbar_init(bar_g, 1);
@@ -484,7 +492,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     named_bar_sync(NB_MATH, BWD_MATH_THREADS);  // s_delta / s_lse visible; O consumed before P overwrites it
     TRACE_MARK();  // delta
     uint32_t ph_sd = 0, ph_g = 0;
-    int g_pending = 0;
+    int g_pending = 0, epi_j = -1;
+    // Gradient tiles leave through shared memory + one TMA bulk store per [128 rows][64 cols] tile (a
+    // row-per-thread 16-byte global store costs 32 LSU cycles per warp instruction).  Staging space: the K / V
+    // tiles of a finished key tile, and at the very end the Q tiles — all dead once the MMAs that read them
+    // have retired.  The softmax scale is applied here, not per element.
+    auto stage32 = [&](uint8_t* tile, const uint32_t* acc, float mul) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(tile + swz_off(row, half * 4 + g)) =
+            make_uint4(pack_bf16x2(__uint_as_float(acc[8 * g + 0]) * mul, __uint_as_float(acc[8 * g + 1]) * mul),
+                       pack_bf16x2(__uint_as_float(acc[8 * g + 2]) * mul, __uint_as_float(acc[8 * g + 3]) * mul),
+                       pack_bf16x2(__uint_as_float(acc[8 * g + 4]) * mul, __uint_as_float(acc[8 * g + 5]) * mul),
+                       pack_bf16x2(__uint_as_float(acc[8 * g + 6]) * mul, __uint_as_float(acc[8 * g + 7]) * mul));
+    };
+    auto store_dk_dv = [&](int j) {
+      uint32_t a[32], v[32];
+      tmem_ld_32x32b_x32(t_lane + TM_DK + half * 32, a);
+      tmem_ld_32x32b_x32(t_lane + TM_DV + half * 32, v);
+      tmem_ld_wait();
+      stage32(sK + j * TILE16K, a, p.scale);
+      stage32(sV + j * TILE16K, v, 1.0f);
+      fence_proxy_async_smem();
+      named_bar_sync(NB_MATH, BWD_MATH_THREADS);
+      if (threadIdx.x == 0) {
+        tma_store_3d(&tmap_dqkv, sK + j * TILE16K, p.d + h * ATT_DH, j * 128, b);
+        tma_store_3d(&tmap_dqkv, sV + j * TILE16K, 2 * p.d + h * ATT_DH, j * 128, b);
+        tma_store_commit();
+      }
+    };
     for (int n = 0; n < nblocks; ++n) {
       const int j = n / NT, i = n % NT;
       mbar_wait(bar_sd, ph_sd);
@@ -547,12 +583,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         }
       }
       TRACE_MARK();  // softmax / dS math
-      // the previous block's dV/dK/dQ MMAs still read sP / sdS: wait before overwriting them
+      // the previous block's dV/dK/dQ MMAs still read sP / sdS: wait before overwriting them.  If that block
+      // closed a key tile, its dK / dV are final now: drain them here, i.e. AFTER this block's math, so the
+      // MMA batch ran underneath the math instead of being waited for (the MMAs that reuse the dK / dV
+      // columns are only issued after this thread's next SMEM_READY arrive below).
       if (g_pending) {
         mbar_wait(bar_g, ph_g);
         ph_g ^= 1;
         g_pending = 0;
         __syncwarp();
+        if (epi_j >= 0) {
+          tc_fence_after();
+          store_dk_dv(epi_j);
+          epi_j = -1;
+          tc_fence_before();
+        }
       }
       {
         uint8_t* pblk = sP + half * TILE16K;
@@ -569,38 +614,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       fence_proxy_async_smem();
       named_bar_arrive(NB_SMEM_READY, BWD_THREADS);
       g_pending = 1;
-
-      if (i == NT - 1) {
-        // ---- dK_j, dV_j complete: TMEM -> bf16 -> dqkv (the softmax scale is applied here, not per element) ----
-        mbar_wait(bar_g, ph_g);
-        ph_g ^= 1;
-        g_pending = 0;
-        __syncwarp();
-        tc_fence_after();
-        uint32_t a[32], v[32];
-        tmem_ld_32x32b_x32(t_lane + TM_DK + half * 32, a);
-        tmem_ld_32x32b_x32(t_lane + TM_DV + half * 32, v);
-        tmem_ld_wait();
-        const int key = j * 128 + row;
-        if (key < p.S) {
-          __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.S + key) * (3 * p.d) + h * ATT_DH + half * 32;
-          store_acc32(base + p.d, a, p.scale);
-          store_acc32(base + 2 * p.d, v, 1.0f);
-        }
-        tc_fence_before();  // ordered before this thread's next named-barrier arrive, which precedes the MMAs that reuse dK / dV
-      }
+      if (i == NT - 1) epi_j = j;  // dK_j / dV_j complete once this block's MMAs retire
     }
-    // ---- dQ (the last block's bar_g wait above covers every MMA) ----
+    // ---- last key tile's dK / dV, then dQ (this bar_g wait covers every MMA) ----
+    mbar_wait(bar_g, ph_g);
+    __syncwarp();
     tc_fence_after();
+    store_dk_dv(epi_j);
     for (int i = 0; i < NT; ++i) {
       uint32_t a[32];
       tmem_ld_32x32b_x32(t_lane + TM_DQ + i * ATT_DH + half * 32, a);
       tmem_ld_wait();
-      const int q = i * 128 + row;
-      if (q < p.S) {
-        __nv_bfloat16* base = p.dqkv + (static_cast<long long>(b) * p.S + q) * (3 * p.d) + h * ATT_DH + half * 32;
-        store_acc32(base, a, p.scale);
-      }
+      stage32(sQ + i * TILE16K, a, p.scale);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(NB_MATH, BWD_MATH_THREADS);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < NT; ++i) tma_store_3d(&tmap_dqkv, sQ + i * TILE16K, h * ATT_DH, i * 128, b);
+      tma_store_commit();
+      tma_store_wait<0>();  // shared memory must outlive the bulk stores that read it
     }
   }
   tc_fence_before();
@@ -645,18 +677,21 @@ extern "C" int m3p_attention_fwd(const m3p_attn_args* a, m3p_stream_t stream_) {
   AttnKernelParams p{};
   int rc = fill_params(a, p, "m3p_attention_fwd");
   if (rc) return rc;
-  CUtensorMap tq, tkv;
+  CUtensorMap tq, tkv, tctx;
   const uint64_t d3 = 3ull * p.d;
   rc = get_tmap_3d_bf16(&tq, a->qkv, d3, (uint64_t)p.S, (uint64_t)p.B, d3, d3 * p.S, ATT_DH, 128, 1);
   if (rc) return rc;
   rc = get_tmap_3d_bf16(&tkv, a->qkv, d3, (uint64_t)p.S, (uint64_t)p.B, d3, d3 * p.S, ATT_DH, 256, 1);
+  if (rc) return rc;
+  rc = get_tmap_3d_bf16(&tctx, a->ctx, (uint64_t)p.d, (uint64_t)p.S, (uint64_t)p.B, (uint64_t)p.d, (uint64_t)p.d * p.S,
+                        ATT_DH, 128, 1);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     M3P_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_BYTES));
     attr_set = true;
   }
-  attn_fwd_kernel<<<p.B * p.H * p.MT, FWD_THREADS, FWD_SMEM_BYTES, stream>>>(tq, tkv, p);
+  attn_fwd_kernel<<<p.B * p.H * p.MT, FWD_THREADS, FWD_SMEM_BYTES, stream>>>(tq, tkv, tctx, p);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }
@@ -667,7 +702,7 @@ extern "C" int m3p_attention_bwd(const m3p_attn_args* a, m3p_stream_t stream_) {
   int rc = fill_params(a, p, "m3p_attention_bwd");
   if (rc) return rc;
   M3P_REQUIRE(a->dctx && a->dqkv, "m3p_attention_bwd: dctx / dqkv missing");
-  CUtensorMap tqkv, tdo, to;
+  CUtensorMap tqkv, tdo, to, tdq;
   const uint64_t d3 = 3ull * p.d, d1 = (uint64_t)p.d;
   rc = get_tmap_3d_bf16(&tqkv, a->qkv, d3, (uint64_t)p.S, (uint64_t)p.B, d3, d3 * p.S, ATT_DH, 256, 1);
   if (rc) return rc;
@@ -675,12 +710,14 @@ extern "C" int m3p_attention_bwd(const m3p_attn_args* a, m3p_stream_t stream_) {
   if (rc) return rc;
   rc = get_tmap_3d_bf16(&to, a->ctx, d1, (uint64_t)p.S, (uint64_t)p.B, d1, d1 * p.S, ATT_DH, 256, 1);
   if (rc) return rc;
+  rc = get_tmap_3d_bf16(&tdq, a->dqkv, d3, (uint64_t)p.S, (uint64_t)p.B, d3, d3 * p.S, ATT_DH, 128, 1);
+  if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     M3P_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
     attr_set = true;
   }
-  attn_bwd_kernel<<<p.B * p.H, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(tqkv, tdo, to, p);
+  attn_bwd_kernel<<<p.B * p.H, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(tqkv, tdo, to, tdq, p);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }
