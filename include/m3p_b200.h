@@ -46,6 +46,11 @@ M3P_API int m3p_version(void);
 M3P_API const char* m3p_last_error(void);
 /* 0 iff the current CUDA device is compute capability 10.x (the only target; no fallback). */
 M3P_API int m3p_device_check(void);
+/* Dropout seeds: every entry point with a `seed` uses seed ^ *device_word (read on the device at kernel
+ * start) once a word has been registered here (NULL unregisters).  The launch parameters of a step can
+ * then stay constant — e.g. inside a captured CUDA graph — while the caller advances the word between
+ * steps to draw fresh masks; forward and backward of one step must see the same value. */
+M3P_API int m3p_set_seed_mix(const uint64_t* device_word);
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core GEMM (tcgen05.mma, TMA-staged, fp32 accumulation in TMEM) with fused epilogue.

@@ -36,6 +36,9 @@ int sm_count() {
   return n;
 }
 
+static const uint64_t* g_seed_mix = nullptr;
+const uint64_t* seed_mix_ptr() { return g_seed_mix; }
+
 float* scratch_f32(size_t n_floats) {
   static float* buf = nullptr;
   static size_t cap = 0;
@@ -150,7 +153,12 @@ int get_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t 
 
 }  // namespace m3p
 
-extern "C" int m3p_version(void) { return 100; }
+extern "C" int m3p_version(void) { return 101; }
+
+extern "C" int m3p_set_seed_mix(const uint64_t* device_word) {
+  m3p::g_seed_mix = device_word;
+  return M3P_OK;
+}
 
 extern "C" const char* m3p_last_error(void) { return m3p::tls_error; }
 

@@ -57,6 +57,7 @@ struct AttnKernelParams {
   const __nv_bfloat16* dctx;     // backward
   __nv_bfloat16* dqkv;           // backward
   uint32_t thr16, seed_lo, seed_hi;
+  const uint64_t* seed_mix;
   float drop_scale;
 };
 
@@ -185,6 +186,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     L = L < 0 ? 0 : (L > p.S ? p.S : L);
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
     const int nfull = L >> 5;  // chunks with every key valid
+    uint32_t seed_lo = p.seed_lo, seed_hi = p.seed_hi;
+    if (p.thr16 != 0) mix_seed(p.seed_mix, seed_lo, seed_hi);
     TRACE_MARK();  // setup
     mbar_wait(bar_s, 0);
     __syncwarp();
@@ -248,7 +251,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             const uint32_t e0 = attn_drop_base(bh, q_idx, c * 32) >> 1;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const uint32_t hsh = drop_hash(e0 + j, p.seed_lo, p.seed_hi);
+              const uint32_t hsh = drop_hash(e0 + j, seed_lo, seed_hi);
               pv[2 * j] = ((hsh & 0xffffu) >= p.thr16) ? pv[2 * j] : 0.f;
               pv[2 * j + 1] = ((hsh >> 16) >= p.thr16) ? pv[2 * j + 1] : 0.f;
             }
@@ -463,6 +466,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const int w4 = warp & 3, half = warp >> 2;
     const int row = w4 * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
+    uint32_t seed_lo = p.seed_lo, seed_hi = p.seed_hi;
+    if (p.thr16 != 0) mix_seed(p.seed_mix, seed_lo, seed_hi);
     {
       const int r = threadIdx.x;
       s_lse[r] = (r < p.S) ? p.lse[static_cast<long long>(bh) * p.S + r] : INFINITY;  // phantom rows: exp2(-inf) = 0
@@ -563,7 +568,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             const uint32_t e0 = attn_drop_base(bh, q, key0) >> 1;
 #pragma unroll
             for (int jp = 0; jp < 16; ++jp) {
-              const uint32_t hsh = drop_hash(e0 + jp, p.seed_lo, p.seed_hi);
+              const uint32_t hsh = drop_hash(e0 + jp, seed_lo, seed_hi);
               const float k0 = ((hsh & 0xffffu) >= p.thr16) ? p.drop_scale : 0.f;
               const float k1 = ((hsh >> 16) >= p.thr16) ? p.drop_scale : 0.f;
               ds[2 * jp] = pd[2 * jp] * fmaf(__uint_as_float(dacc[2 * jp]), k0, -delta);
@@ -665,6 +670,7 @@ static int fill_params(const m3p_attn_args* a, AttnKernelParams& p, const char* 
   p.drop_scale = 1.0f / (1.0f - a->drop_p);
   p.seed_lo = (uint32_t)(a->seed & 0xffffffffu);
   p.seed_hi = (uint32_t)(a->seed >> 32);
+  p.seed_mix = seed_mix_ptr();
   return M3P_OK;
 }
 

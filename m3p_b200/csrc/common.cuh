@@ -47,6 +47,17 @@ float* scratch_f32(size_t n_floats);
 // out_k[col] += sum_p partial[p][k * seg + col]  for k < nout; second stage of the reductions above.
 int reduce_partials(const float* partial, int parts, int seg, float* const* outs, int nout, cudaStream_t stream);
 
+// Device word XOR-ed into every dropout seed at kernel start (m3p_set_seed_mix): lets a captured CUDA graph
+// replay with fresh masks — the caller bumps the word between replays, the launch parameters stay constant.
+const uint64_t* seed_mix_ptr();  // api.cu; NULL when unset
+__device__ __forceinline__ void mix_seed(const uint64_t* mix, uint32_t& lo, uint32_t& hi) {
+  if (mix != nullptr) {
+    const uint64_t m = *mix;
+    lo ^= static_cast<uint32_t>(m);
+    hi ^= static_cast<uint32_t>(m >> 32);
+  }
+}
+
 // ---- dropout generator -------------------------------------------------------------------------
 // One 32-bit hash per PAIR of consecutive elements; each 16-bit half decides one element:
 // keep iff half >= thr16, thr16 = round(p * 65536).  Element index is the row-major linear index

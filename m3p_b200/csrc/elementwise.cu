@@ -150,6 +150,7 @@ struct LnBwdParams {
   void* dx; __nv_bfloat16* dx_drop;
   uint32_t dx_thr16, dx_seed_lo, dx_seed_hi; float dx_scale;
   uint32_t dy_thr16, dy_seed_lo, dy_seed_hi; float dy_scale;
+  const uint64_t* seed_mix;
   float* dgamma; float* dbeta; float* dbias;
   float* partial;  // [gridDim.x][3][d] scratch: per-CTA column sums (dgamma | dbeta | dbias)
   long long rows; int d;
@@ -168,6 +169,9 @@ ln_bwd_dx_kernel(const LnBwdParams p) {
   const XT* x = reinterpret_cast<const XT*>(p.x);
   const DYT* dy = reinterpret_cast<const DYT*>(p.dy);
   DXT* dx = reinterpret_cast<DXT*>(p.dx);
+  uint32_t dy_lo = p.dy_seed_lo, dy_hi = p.dy_seed_hi, dx_lo = p.dx_seed_lo, dx_hi = p.dx_seed_hi;
+  if (p.dy_thr16 != 0) mix_seed(p.seed_mix, dy_lo, dy_hi);
+  if (p.dx_thr16 != 0) mix_seed(p.seed_mix, dx_lo, dx_hi);
   for (long long row = warp0; row < p.rows; row += nwarps) {
     bool valid = true;
     if (p.seqlen != nullptr) valid = (row % p.S) < p.seqlen[row / p.S];
@@ -183,7 +187,7 @@ ln_bwd_dx_kernel(const LnBwdParams p) {
         load8(dy + row * d + ch * 8, dv);
         load8(p.gamma + ch * 8, gm);
         if (p.dy_thr16 != 0)
-          drop8((uint32_t)row * (uint32_t)d + ch * 8, p.dy_seed_lo, p.dy_seed_hi, p.dy_thr16, p.dy_scale, dv);
+          drop8((uint32_t)row * (uint32_t)d + ch * 8, dy_lo, dy_hi, p.dy_thr16, p.dy_scale, dv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[c][j] = (xv[j] - mean) * rstd;
@@ -205,7 +209,7 @@ ln_bwd_dx_kernel(const LnBwdParams p) {
         store8(dx + row * d + ch * 8, o);
         if (p.dx_drop != nullptr) {
           if (p.dx_thr16 != 0)
-            drop8((uint32_t)row * (uint32_t)d + ch * 8, p.dx_seed_lo, p.dx_seed_hi, p.dx_thr16, p.dx_scale, o);
+            drop8((uint32_t)row * (uint32_t)d + ch * 8, dx_lo, dx_hi, p.dx_thr16, p.dx_scale, o);
           store8(p.dx_drop + row * d + ch * 8, o);
         }
       }
@@ -259,6 +263,8 @@ ln_bwd_cols_kernel(const LnBwdParams p, const BT* __restrict__ bias_src, int tx,
 #pragma unroll
   for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; abias[j] = 0.f; }
   const bool want_gb = (p.dgamma != nullptr) || (p.dbeta != nullptr);
+  uint32_t dy_lo = p.dy_seed_lo, dy_hi = p.dy_seed_hi;
+  if (p.dy_thr16 != 0) mix_seed(p.seed_mix, dy_lo, dy_hi);
   if (col_ok) {
     for (long long r = r0 + ry; r < r1; r += 2 * ty) {
       float xv[2][8], dv[2][8], bv[2][8], mean[2], rstd[2];
@@ -285,7 +291,7 @@ ln_bwd_cols_kernel(const LnBwdParams p, const BT* __restrict__ bias_src, int tx,
           if (p.seqlen != nullptr) valid = (row % p.S) < p.seqlen[row / p.S];
           if (valid) {
             if (p.dy_thr16 != 0)
-              drop8((uint32_t)row * (uint32_t)d + col0, p.dy_seed_lo, p.dy_seed_hi, p.dy_thr16, p.dy_scale, dv[i]);
+              drop8((uint32_t)row * (uint32_t)d + col0, dy_lo, dy_hi, p.dy_thr16, p.dy_scale, dv[i]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               ag[j] = fmaf(dv[i][j], (xv[i][j] - mean[i]) * rstd[i], ag[j]);
@@ -681,6 +687,7 @@ extern "C" int m3p_layernorm_bwd(const m3p_ln_bwd_args* a, m3p_stream_t stream_)
   p.dy_thr16 = a->dy_drop_p > 0.f ? drop_thr16(a->dy_drop_p) : 0;
   p.dy_scale = 1.0f / (1.0f - a->dy_drop_p);
   p.dy_seed_lo = (uint32_t)(a->dy_seed & 0xffffffffu); p.dy_seed_hi = (uint32_t)(a->dy_seed >> 32);
+  p.seed_mix = seed_mix_ptr();
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dbias = a->dbias;
   p.rows = a->rows; p.d = (int)a->d;
   const int key = (a->x_f32 ? 4 : 0) | (a->dy_f32 ? 2 : 0) | (a->dx_f32 ? 1 : 0);

@@ -37,7 +37,7 @@ constexpr int EMB_WARPS = EMB_THREADS / 32;
 
 template <int MAXC>
 __global__ void __launch_bounds__(EMB_THREADS)
-embed_fwd_kernel(const m3p_embed_args a, const uint32_t thr16, const float scale) {
+embed_fwd_kernel(const m3p_embed_args a, const uint32_t thr16, const float scale, const uint64_t* seed_mix) {
   const int lane = threadIdx.x & 31;
   const int d = (int)a.d;
   const int nchunks = d >> 3;
@@ -45,8 +45,12 @@ embed_fwd_kernel(const m3p_embed_args a, const uint32_t thr16, const float scale
   const long long rows = a.B * S;
   const long long warp0 = (long long)blockIdx.x * EMB_WARPS + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * EMB_WARPS;
-  const uint32_t si_lo = (uint32_t)(a.seed_img & 0xffffffffu), si_hi = (uint32_t)(a.seed_img >> 32);
-  const uint32_t se_lo = (uint32_t)(a.seed_emb & 0xffffffffu), se_hi = (uint32_t)(a.seed_emb >> 32);
+  uint32_t si_lo = (uint32_t)(a.seed_img & 0xffffffffu), si_hi = (uint32_t)(a.seed_img >> 32);
+  uint32_t se_lo = (uint32_t)(a.seed_emb & 0xffffffffu), se_hi = (uint32_t)(a.seed_emb >> 32);
+  if (thr16 != 0) {
+    mix_seed(seed_mix, si_lo, si_hi);
+    mix_seed(seed_mix, se_lo, se_hi);
+  }
   __nv_bfloat16* h0 = reinterpret_cast<__nv_bfloat16*>(a.h0);
 
   for (long long row = warp0; row < rows; row += nwarps) {
@@ -296,9 +300,9 @@ extern "C" int m3p_embed_fwd(const m3p_embed_args* a, m3p_stream_t stream_) {
   long long g = (rows + EMB_WARPS - 1) / EMB_WARPS;
   const long long cap = (long long)sm_count() * 8;
   const int grid = (int)(g < cap ? g : cap);
-  if (a->d <= 256) embed_fwd_kernel<1><<<grid, EMB_THREADS, 0, stream>>>(*a, thr16, scale);
-  else if (a->d <= 768) embed_fwd_kernel<3><<<grid, EMB_THREADS, 0, stream>>>(*a, thr16, scale);
-  else embed_fwd_kernel<4><<<grid, EMB_THREADS, 0, stream>>>(*a, thr16, scale);
+  if (a->d <= 256) embed_fwd_kernel<1><<<grid, EMB_THREADS, 0, stream>>>(*a, thr16, scale, seed_mix_ptr());
+  else if (a->d <= 768) embed_fwd_kernel<3><<<grid, EMB_THREADS, 0, stream>>>(*a, thr16, scale, seed_mix_ptr());
+  else embed_fwd_kernel<4><<<grid, EMB_THREADS, 0, stream>>>(*a, thr16, scale, seed_mix_ptr());
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }

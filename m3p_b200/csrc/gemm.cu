@@ -46,6 +46,7 @@ struct GemmKernelParams {
   long long ldaux;
   float drop_scale;
   uint32_t thr16, seed_lo, seed_hi;
+  const uint64_t* seed_mix;
   int accumulate;
   int vec_ok;  // all pitches / bases allow 16-byte vector access
   int tma_store;  // bf16 outputs leave through smem staging + cp.async.bulk.tensor stores
@@ -101,7 +102,8 @@ __device__ __forceinline__ void stage_bf16x16(uint8_t* stg, int r, int chunk_in_
 template <int EPI, bool OUT_F32>
 __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const uint32_t* acc, const float* sbias,
                                                const uint4* auxr, long long row, int col0, int ncols,
-                                               uint8_t* stg, uint8_t* stg2, int lane, int chunk_in_group) {
+                                               uint8_t* stg, uint8_t* stg2, int lane, int chunk_in_group,
+                                               uint32_t seed_lo, uint32_t seed_hi) {
   float v[EW];
   const bool full = (ncols == EW) && p.vec_ok;
   // v = alpha * acc + bias
@@ -131,14 +133,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
         if ((e0 & 1u) == 0) {
 #pragma unroll
           for (int j = 0; j < EW / 2; ++j) {
-            const uint32_t h = drop_hash((e0 >> 1) + j, p.seed_lo, p.seed_hi);
+            const uint32_t h = drop_hash((e0 >> 1) + j, seed_lo, seed_hi);
             v[2 * j] = ((h & 0xffffu) >= p.thr16) ? v[2 * j] * p.drop_scale : 0.f;
             v[2 * j + 1] = ((h >> 16) >= p.thr16) ? v[2 * j + 1] * p.drop_scale : 0.f;
           }
         } else {
 #pragma unroll
           for (int j = 0; j < EW; ++j)
-            v[j] = drop_keep(e0 + j, p.seed_lo, p.seed_hi, p.thr16) ? v[j] * p.drop_scale : 0.f;
+            v[j] = drop_keep(e0 + j, seed_lo, seed_hi, p.thr16) ? v[j] * p.drop_scale : 0.f;
         }
       }
 #pragma unroll
@@ -381,6 +383,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr int NCH = BN / 2 / EW;       // chunks per warp
     const int cbase = half * (BN / 2);
     float* sbias = bias_smem + (warp_idx - 4) * (BN / 2);
+    uint32_t seed_lo = p.seed_lo, seed_hi = p.seed_hi;
+    if constexpr (EPI == M3P_EPI_DROP_RES) mix_seed(p.seed_mix, seed_lo, seed_hi);
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     for (int u = unit0; u < p.num_units; u += unit_stride) {
@@ -444,7 +448,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           // rows / columns outside the problem are clipped by the TMA store; skip their math (and aux reads)
           if (row_ok && col0 < p.N)
             epilogue_chunk<EPI, OUT_F32>(p, acc[ii], sbias + i * EW, ax, row, col0, min(EW, p.N - col0), stg, stg2,
-                                         lane, i & 3);
+                                         lane, i & 3, seed_lo, seed_hi);
           if ((i & 3) == 3) {
             fence_proxy_async_smem();
             __syncwarp();
@@ -456,7 +460,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         } else if (row_ok && col0 < p.N) {
           epilogue_chunk<EPI, OUT_F32>(p, acc[ii], sbias + i * EW, ax, row, col0, min(EW, p.N - col0), nullptr,
-                                       nullptr, lane, 0);
+                                       nullptr, lane, 0, seed_lo, seed_hi);
         }
       };
       if constexpr (HAS_AUX) {
@@ -627,6 +631,7 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   p.drop_scale = 1.0f / (1.0f - a->drop_p);
   p.seed_lo = (uint32_t)(a->seed & 0xffffffffu);
   p.seed_hi = (uint32_t)(a->seed >> 32);
+  p.seed_mix = seed_mix_ptr();
   p.accumulate = a->accumulate;
   {
     const int osz = a->out_f32 ? 4 : 2;

@@ -84,6 +84,7 @@ class EmbedBwdArgs(ctypes.Structure):
 # (tests/test_abi.py checks this table against the header).
 PROTOTYPES = {
     "m3p_device_check": [],
+    "m3p_set_seed_mix": [c_void_p],
     "m3p_gemm_bf16": [POINTER(GemmArgs), c_void_p],
     "m3p_gemm_bf16_debug": [POINTER(GemmArgs)] + [c_int32] * 6 + [c_void_p],
     "m3p_attention_fwd": [POINTER(AttnArgs), c_void_p],

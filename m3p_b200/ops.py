@@ -17,10 +17,24 @@ LAUNCHES = 0  # kernels of libm3p_sm100.so enqueued by this process (every entry
               # m3p_cross_entropy_fwd two); bench.py reports the per-step delta as `gpu_launches`
 
 
+_STREAM = None  # cached c_void_p of the stream to enqueue on (torch.cuda.current_stream() costs ~15 us per call)
+
+
+def use_current_stream():
+    """Latch torch's current CUDA stream for the calls that follow.  Every entry point of the host layer
+    (encoder forward / backward, each head) calls this once, so stream contexts and CUDA-graph capture
+    are honoured without paying the lookup on each of the ~300 kernel launches of a step."""
+    global _STREAM
+    _STREAM = _vp(torch.cuda.current_stream().cuda_stream)
+    return _STREAM
+
+
 def _stream():
     global LAUNCHES
     LAUNCHES += 1
-    return _vp(torch.cuda.current_stream().cuda_stream)
+    if _STREAM is None:
+        return use_current_stream()
+    return _STREAM
 
 
 def _p(t):

@@ -114,3 +114,44 @@ def synthetic_batch(B, T, R, n_words, sample_n=4, seed=1234, ragged=False, n_mas
     if device != "cpu":
         batch = {k: v.to(device) for k, v in batch.items()}
     return batch
+
+
+class GraphedStep:
+    """One training step (zero_grad + forward + loss + backward) captured ONCE into a CUDA graph and replayed:
+    ~320 kernel launches collapse into a single graph launch, removing the host from the step.  Inputs are
+    static device tensors (`self.batch`); `step(new_batch)` copies a new batch into them first (H2D from pinned
+    host memory is asynchronous).  Dropout stays fresh across replays because the seeds live in a device word
+    bumped inside the graph (TransformerModel._next_seed)."""
+
+    def __init__(self, model, batch, sample_n=4, heads=("rel",), lambdas=None, warmup=3, after_backward=None):
+        self.model, self.batch = model, {k: v.clone() for k, v in batch.items()}
+        self.sample_n, self.heads, self.lambdas, self.after_backward = sample_n, heads, lambdas, after_backward
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up off the default stream: allocations, kernel attributes, scratch
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        from . import ops
+        n0 = ops.LAUNCHES
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager()
+        self.launches_per_step = ops.LAUNCHES - n0
+
+    def _eager(self):
+        self.model.zero_grad()
+        total, _ = pretrain_step(self.model, self.batch, self.sample_n, self.heads, self.lambdas)
+        total.backward()
+        if self.after_backward is not None:
+            self.after_backward()
+        return total.detach()
+
+    def step(self, new_batch=None):
+        if new_batch is not None:
+            for k, v in new_batch.items():
+                if k in self.batch:
+                    self.batch[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.loss

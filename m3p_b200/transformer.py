@@ -106,7 +106,9 @@ class TransformerModel(nn.Module):
                                       "got %d" % (self.dim // self.n_heads))
         self._seed_base = 0x5DEECE66D
         self._step = 0
+        self._seed_words = None
         self._grad_ready_hook = None  # set by ddp.GradReducer: (name, lo, hi) slice of _flat_grad is final
+        self._device_checked = False
         self._emb_touched = None      # token-id tensors scattered into _emb_grad since it was last cleared
         self._emb_dense_dirty = True  # True once a dense update (tied MLM head) or foreign writer touched it
         self._build_parameters()
@@ -304,6 +306,7 @@ class TransformerModel(nn.Module):
 
     def refresh_operands(self, embeddings=False):
         """bf16 tensor-core copies of the fp32 masters (one cast kernel over the flat buffer)."""
+        ops.use_current_stream()
         if self._flat16 is None:
             self._flat16 = torch.empty(self._flat_numel, dtype=_BF16, device=self._flat.device)
         ops.cast_f32_bf16(self._flat, self._flat16, self._flat_numel)
@@ -377,9 +380,24 @@ class TransformerModel(nn.Module):
     def _drop(self):
         return (self.dropout if self.training else 0.0), (self.attention_dropout if self.training else 0.0)
 
+    _SEED_SLOTS = 8
+    _SEED_INC = 0x1E3779B97F4A7C15  # odd: the per-call device word walks through all 2^64 values
+
     def _next_seed(self):
+        """Dropout seeding that survives CUDA-graph replay: the host-side seed is a constant, the per-call
+        variation lives in a device word that this call bumps (one tiny kernel, captured with the graph)
+        and registers with the library (m3p_set_seed_mix); kernels XOR it in at start.  A ring of words
+        lets several forwards be in flight before their backwards (e.g. the CLCM second pass) — the
+        backward re-registers the word its forward used.  Returns (host seed, device word tensor)."""
+        if self._seed_words is None or self._seed_words.device != self._flat.device:
+            self._seed_words = torch.zeros(self._SEED_SLOTS, dtype=torch.int64, device=self._flat.device)
+        slot = self._step % self._SEED_SLOTS
         self._step += 1
-        return (self._seed_base + self._step * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        word = self._seed_words[slot:slot + 1]
+        if self.training:
+            word.add_(self._SEED_INC)
+        L.load().m3p_set_seed_mix(word.data_ptr())
+        return self._seed_base, word
 
     def _require_cuda(self, t):
         if not t.is_cuda:
@@ -503,7 +521,10 @@ class TransformerModel(nn.Module):
 
     def _encode(self, spec, x_img, text_embed, need_grad):
         """Forward of the embedding stage + layer loop.  Returns (h [B*S, d] bf16, stash)."""
-        ops.device_check()
+        ops.use_current_stream()
+        if not self._device_checked:
+            ops.device_check()
+            self._device_checked = True
         dev = self._flat.device
         B, T, R, d, H = spec["B"], spec["T"], spec["R"], self.dim, self.n_heads
         S = R + T
@@ -511,12 +532,12 @@ class TransformerModel(nn.Module):
         if S > 256:
             raise NotImplementedError("sequence length %d > 256 is not supported by the fused attention kernel" % S)
         p_drop, p_att = self._drop()
-        seed = self._next_seed()
+        seed, seed_word = self._next_seed()
         self.refresh_operands()
         e = lambda *s, dt=_BF16: torch.empty(*s, dtype=dt, device=dev)
         seqlen = spec["lengths"].to(device=dev, dtype=torch.int32).contiguous()
-        st = dict(spec=spec, seqlen=seqlen, seed=seed, p_drop=p_drop, p_att=p_att, B=B, T=T, R=R, S=S, M=M,
-                  need_grad=need_grad, layers=[])
+        st = dict(spec=spec, seqlen=seqlen, seed=seed, seed_word=seed_word, p_drop=p_drop, p_att=p_att, B=B, T=T, R=R,
+                  S=S, M=M, need_grad=need_grad, layers=[])
 
         # ---- embedding stage (transformer.py:897-943 / 820-831 / 1044-1062) ----
         a = L.EmbedArgs()
@@ -603,6 +624,8 @@ class TransformerModel(nn.Module):
     def _encode_backward(self, st, dh, want_dximg, want_dtext):
         """Backward of `_encode`: dh [B*S, d] bf16 -> parameter gradients (accumulated into the flat
         buffer) and, on request, d x_img (R,B,2048) / d text_embed (B,T,d) for FreeLB."""
+        ops.use_current_stream()
+        L.load().m3p_set_seed_mix(st["seed_word"].data_ptr())  # the masks this forward drew
         self.attach_grads()
         dev = self._flat.device
         B, T, R, S, M, d, H = st["B"], st["T"], st["R"], st["S"], st["M"], self.dim, self.n_heads
@@ -750,6 +773,7 @@ class _RelationFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, tensor, model, pl, sr, token):
+        ops.use_current_stream()
         dev = tensor.device
         t = tensor if tensor.dtype == _BF16 else tensor.to(_BF16)
         B, S, d = t.shape
@@ -767,6 +791,7 @@ class _RelationFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dscores):
+        ops.use_current_stream()
         model = ctx.model
         pl, sr = ctx.names
         first, pooled, idx = ctx.saved_tensors
@@ -793,6 +818,7 @@ class _MrfrFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, tensor, model, token):
+        ops.use_current_stream()
         dev = tensor.device
         t = tensor if tensor.dtype == _BF16 else tensor.to(_BF16)
         B, R, d = t.shape
@@ -807,6 +833,7 @@ class _MrfrFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        ops.use_current_stream()
         model = ctx.model
         (rows,) = ctx.saved_tensors
         B, R, d = ctx.shape
@@ -827,6 +854,7 @@ class _ObjFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, tensor, y, model, get_scores, token):
+        ops.use_current_stream()
         dev = tensor.device
         t = tensor if tensor.dtype == _BF16 else tensor.to(_BF16)
         B, R, d = t.shape
@@ -855,6 +883,7 @@ class _ObjFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, _dscores, dloss):
+        ops.use_current_stream()
         model = ctx.model
         rows, gp, g, tn, mean, rstd, logits, yv, lse, inv = ctx.saved_tensors
         B, R, d = ctx.shape
@@ -888,6 +917,7 @@ class _MlmFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, tensor, pred_mask, y, model, get_scores, token):
+        ops.use_current_stream()
         dev = tensor.device
         t = tensor if tensor.dtype == _BF16 else tensor.to(_BF16)
         slen, bs, d = t.shape
@@ -913,6 +943,7 @@ class _MlmFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, _dscores, dloss):
+        ops.use_current_stream()
         model = ctx.model
         rows, logits, yv, lse, inv, idx = ctx.saved_tensors
         slen, bs, d, n = ctx.shape

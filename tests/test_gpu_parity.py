@@ -421,3 +421,34 @@ def test_gemm_fused_epilogues(m3p):
     assert _rel(o, (ref - bias) * aux.float()) < KERNEL_TOL
     ops.gemm(A, B, m, n, k, o, bias=bias, epi=L.M3P_EPI_TANH, alpha=0.1)
     assert _rel(o, torch.tanh(0.1 * (ref - bias) + bias)) < KERNEL_TOL
+
+
+def test_cuda_graph_step_matches_eager_and_redraws_dropout(m3p):
+    """GraphedStep: the captured step reproduces the eager gradients, accepts new inputs, and — because the
+    dropout seeds live in a device word bumped inside the graph — draws new masks on every replay."""
+    from m3p_b200.train_step import GraphedStep, pretrain_step, synthetic_batch
+    ns = _ns(128, 2, 2, 500)
+    b1 = synthetic_batch(4, 12, 5, ns.n_words, sample_n=2, seed=2, n_mask_text=2, n_mask_img=1, device="cuda")
+    b2 = synthetic_batch(4, 12, 5, ns.n_words, sample_n=2, seed=3, n_mask_text=2, n_mask_img=1, device="cuda")
+    eager = _model(m3p, ns)
+    want = []
+    for b in (b1, b2):
+        eager.zero_grad()
+        t, _ = pretrain_step(eager, b, 2)
+        t.backward()
+        want.append((float(t.detach()), eager._flat_grad.clone(), eager._emb_grad.clone()))
+    model = _model(m3p, ns)
+    g = GraphedStep(model, b1, 2, heads=("mlm", "mrm", "mrfr", "rel"))
+    for b, (loss, flat, emb) in zip((b1, b2), want):
+        got = g.step(b)
+        torch.cuda.synchronize()
+        assert abs(float(got) - loss) < 1e-3 * abs(loss)
+        assert _rel(model._flat_grad, flat) < 1e-3 and _rel(model._emb_grad, emb) < 1e-3
+    # with dropout the same graph gives a different loss on every replay, and stays finite
+    drop = _model(m3p, _ns(128, 2, 2, 500, dropout=0.1))
+    gd = GraphedStep(drop, b1, 2, heads=("rel",))
+    losses = []
+    for _ in range(3):
+        losses.append(float(gd.step()))
+        torch.cuda.synchronize()
+    assert len(set(losses)) == 3 and all(l == l for l in losses)
