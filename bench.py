@@ -161,6 +161,7 @@ def workload_name(heads):
 def time_dominant_kernel(torch, ops, L):
     """The FFN GEMM (M=14592, N=3072, K=768; 2/3 of the linear FLOPs are this shape or its transposes)
     timed alone with CUDA events: the `roofline.dominant_kernel` entry."""
+    ops.use_current_stream()  # the step ran on the graph's capture stream: latch torch's current stream again
     m, n, k = 14592, 3072, 768
     a = torch.randn(m, k, device="cuda").to(torch.bfloat16)
     w = torch.randn(n, k, device="cuda").to(torch.bfloat16)

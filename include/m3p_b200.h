@@ -174,6 +174,11 @@ typedef struct m3p_ln_bwd_args {
   int32_t x_f32, dy_f32, dx_f32;
 } m3p_ln_bwd_args;
 M3P_API int m3p_layernorm_bwd(const m3p_ln_bwd_args* args, m3p_stream_t stream);
+/* The two passes of m3p_layernorm_bwd on their own, so a caller can put the parameter-gradient column
+ * pass (dgamma / dbeta / dbias; reads dy, x, mean, rstd and the dx / dx_drop the row pass wrote) on a
+ * second stream underneath the GEMMs that continue the activation-gradient chain. */
+M3P_API int m3p_layernorm_bwd_rows(const m3p_ln_bwd_args* args, m3p_stream_t stream);
+M3P_API int m3p_layernorm_bwd_cols(const m3p_ln_bwd_args* args, m3p_stream_t stream);
 
 /* out[j] += sum_rows x[row][j]   (bias gradients of q/k/v and lin1: autograd of :178-181,223) */
 M3P_API int m3p_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int64_t n, m3p_stream_t stream);

@@ -119,8 +119,11 @@ static int encode_cached(CUtensorMap* out, const void* ptr, int rank, const uint
       set_last_error("TMA: row pitch %llu bytes is not a multiple of 16", (unsigned long long)gstride[i]);
       return M3P_ERR_INVALID_ARGUMENT;
     }
+  // the box's inner extent picks the swizzle: 64 bf16 = 128-byte rows (operand tiles), 32 bf16 = 64-byte rows
+  // (the GEMM epilogue's staging tiles)
+  const CUtensorMapSwizzle swz = (box[0] * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim,
-                  gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,

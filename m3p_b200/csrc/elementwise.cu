@@ -326,13 +326,15 @@ ln_bwd_cols_kernel(const LnBwdParams p, const BT* __restrict__ bias_src, int tx,
 }
 
 template <typename XT, typename DYT, typename DXT>
-static int launch_ln_bwd(LnBwdParams p, cudaStream_t stream) {
-  const int grid = ew_grid(p.rows);
-  if (p.d <= 256) ln_bwd_dx_kernel<XT, DYT, DXT, 1><<<grid, EW_THREADS, 0, stream>>>(p);
-  else if (p.d <= 768) ln_bwd_dx_kernel<XT, DYT, DXT, 3><<<grid, EW_THREADS, 0, stream>>>(p);
-  else ln_bwd_dx_kernel<XT, DYT, DXT, 4><<<grid, EW_THREADS, 0, stream>>>(p);
-  M3P_CUDA_OK(cudaGetLastError());
-  if (!(p.dgamma || p.dbeta || p.dbias)) return M3P_OK;
+static int launch_ln_bwd(LnBwdParams p, cudaStream_t stream, int phases) {
+  if (phases & 1) {
+    const int grid = ew_grid(p.rows);
+    if (p.d <= 256) ln_bwd_dx_kernel<XT, DYT, DXT, 1><<<grid, EW_THREADS, 0, stream>>>(p);
+    else if (p.d <= 768) ln_bwd_dx_kernel<XT, DYT, DXT, 3><<<grid, EW_THREADS, 0, stream>>>(p);
+    else ln_bwd_dx_kernel<XT, DYT, DXT, 4><<<grid, EW_THREADS, 0, stream>>>(p);
+    M3P_CUDA_OK(cudaGetLastError());
+  }
+  if (!(phases & 2) || !(p.dgamma || p.dbeta || p.dbias)) return M3P_OK;
   const ColGeom g = col_geom(p.rows, p.d);
   const dim3 cgrid(g.stripes, g.row_blocks);
   const size_t smem = (size_t)EW_THREADS * 8 * sizeof(float);
@@ -669,7 +671,8 @@ extern "C" int m3p_layernorm_fwd(const void* x, const float* gamma, const float*
   return M3P_OK;
 }
 
-extern "C" int m3p_layernorm_bwd(const m3p_ln_bwd_args* a, m3p_stream_t stream_) {
+// phases: bit 0 = the row pass (dx, dx_drop), bit 1 = the column pass (dgamma, dbeta, dbias)
+static int layernorm_bwd_impl(const m3p_ln_bwd_args* a, m3p_stream_t stream_, int phases) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   M3P_REQUIRE(a && a->dy && a->x && a->mean && a->rstd && a->gamma && a->dx, "m3p_layernorm_bwd: null pointer");
   M3P_REQUIRE(a->rows > 0 && a->d > 0 && a->d % 8 == 0 && a->d <= 1024,
@@ -692,15 +695,27 @@ extern "C" int m3p_layernorm_bwd(const m3p_ln_bwd_args* a, m3p_stream_t stream_)
   p.rows = a->rows; p.d = (int)a->d;
   const int key = (a->x_f32 ? 4 : 0) | (a->dy_f32 ? 2 : 0) | (a->dx_f32 ? 1 : 0);
   switch (key) {
-    case 0: return launch_ln_bwd<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(p, stream);
-    case 5: return launch_ln_bwd<float, __nv_bfloat16, float>(p, stream);
-    case 6: return launch_ln_bwd<float, float, __nv_bfloat16>(p, stream);
-    case 4: return launch_ln_bwd<float, __nv_bfloat16, __nv_bfloat16>(p, stream);
+    case 0: return launch_ln_bwd<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(p, stream, phases);
+    case 5: return launch_ln_bwd<float, __nv_bfloat16, float>(p, stream, phases);
+    case 6: return launch_ln_bwd<float, float, __nv_bfloat16>(p, stream, phases);
+    case 4: return launch_ln_bwd<float, __nv_bfloat16, __nv_bfloat16>(p, stream, phases);
     default:
       set_last_error("m3p_layernorm_bwd: unsupported dtype combination x_f32=%d dy_f32=%d dx_f32=%d", a->x_f32,
                      a->dy_f32, a->dx_f32);
       return M3P_ERR_UNSUPPORTED;
   }
+}
+
+extern "C" int m3p_layernorm_bwd(const m3p_ln_bwd_args* a, m3p_stream_t stream) {
+  return layernorm_bwd_impl(a, stream, 3);
+}
+
+extern "C" int m3p_layernorm_bwd_rows(const m3p_ln_bwd_args* a, m3p_stream_t stream) {
+  return layernorm_bwd_impl(a, stream, 1);
+}
+
+extern "C" int m3p_layernorm_bwd_cols(const m3p_ln_bwd_args* a, m3p_stream_t stream) {
+  return layernorm_bwd_impl(a, stream, 2);
 }
 
 extern "C" int m3p_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int64_t n, m3p_stream_t stream_) {

@@ -22,6 +22,22 @@
 
 namespace m3p {
 
+// Phase timing for kernel bring-up (build with M3P_NVCC_EXTRA=-DM3P_GEMM_TRACE): SM-clock stamps of the producer,
+// MMA and one epilogue warp for the first tiles of a few CTAs.  Never compiled into the product build.
+#ifdef M3P_GEMM_TRACE
+#define GT_DECL long long _gt[24]; int _gn = 0; const long long _g0 = clock64();
+#define GT_MARK() do { if (_gn < 24) _gt[_gn++] = clock64() - _g0; } while (0)
+#define GT_DUMP(role) do { if (blockIdx.x == 0 || blockIdx.x == 2 || blockIdx.x == 100) { \
+    for (int _i = _gn; _i < 24; ++_i) _gt[_i] = 0; \
+    printf(role " cta %d n=%d: %lld %lld %lld %lld | %lld %lld %lld %lld | %lld %lld %lld %lld | %lld %lld %lld %lld | %lld %lld %lld %lld | %lld %lld %lld %lld\n", (int)blockIdx.x, _gn, \
+      _gt[0], _gt[1], _gt[2], _gt[3], _gt[4], _gt[5], _gt[6], _gt[7], _gt[8], _gt[9], _gt[10], _gt[11], _gt[12], _gt[13], _gt[14], _gt[15], \
+      _gt[16], _gt[17], _gt[18], _gt[19], _gt[20], _gt[21], _gt[22], _gt[23]); } } while (0)
+#else
+#define GT_DECL
+#define GT_MARK()
+#define GT_DUMP(role)
+#endif
+
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
@@ -61,8 +77,9 @@ __device__ __forceinline__ void decode_unit(const GemmKernelParams& p, int u, in
 }
 
 // ---- epilogue math on one 16-column chunk held by one thread (one output row) -------------------
-// 16 columns = 32 bytes of bf16 per row: every global access of a thread is one full 32-byte sector.
-constexpr int EW = 16;  // epilogue chunk width (columns)
+constexpr int EW = 16;  // epilogue chunk width (columns): one tcgen05.ld.32x32b.x16
+constexpr int GW = 32;  // staging group width (columns): one [32 rows][64 B] SWIZZLE_64B tile per warp = one TMA box
+constexpr uint32_t STG_TILE = 32 * 64;
 
 __device__ __forceinline__ void unpack_bf16x16(const uint4* t, float* x) {
 #pragma unroll
@@ -84,29 +101,32 @@ __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* p, const float* v) 
 template <int EPI>
 constexpr bool epi_has_aux() { return EPI == M3P_EPI_DROP_RES || EPI == M3P_EPI_DGELU || EPI == M3P_EPI_DTANH; }
 
-// sbias: this chunk's 16 bias values in shared memory (staged once per tile, zero past N);
-// auxr : this chunk's aux values (16 bf16), prefetched one chunk ahead when the fast path applies.
-// 16 bf16 of one row into a [32 rows][128 B] SWIZZLE_128B staging tile (the layout a TMA store expects):
-// 16-byte chunk c16 of row r lives at r*128 + ((c16 ^ (r & 7)) << 4) — conflict-free for a warp.
+// Staging tiles are [32 rows][64 B] in the SWIZZLE_64B layout TMA expects: the 16-byte chunk c16 (0..3) of row r
+// lives at r*64 + ((c16 ^ ((r >> 1) & 3)) << 4) — a warp's row-per-lane 16-byte accesses are conflict-free.
+__device__ __forceinline__ uint32_t stg_off(int r, int c16) {
+  return static_cast<uint32_t>(r) * 64u + (static_cast<uint32_t>(c16 ^ ((r >> 1) & 3)) << 4);
+}
 __device__ __forceinline__ void stage_bf16x16(uint8_t* stg, int r, int chunk_in_group, const float* v) {
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int c16 = chunk_in_group * 2 + h;
-    *reinterpret_cast<uint4*>(stg + r * 128 + ((c16 ^ (r & 7)) << 4)) =
+  for (int h = 0; h < 2; ++h)
+    *reinterpret_cast<uint4*>(stg + stg_off(r, chunk_in_group * 2 + h)) =
         make_uint4(pack_bf16x2(v[8 * h + 0], v[8 * h + 1]), pack_bf16x2(v[8 * h + 2], v[8 * h + 3]),
                    pack_bf16x2(v[8 * h + 4], v[8 * h + 5]), pack_bf16x2(v[8 * h + 6], v[8 * h + 7]));
-  }
+}
+__device__ __forceinline__ void unstage_bf16x16(const uint8_t* stg, int r, int chunk_in_group, float* x) {
+  uint4 t[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) t[h] = *reinterpret_cast<const uint4*>(stg + stg_off(r, chunk_in_group * 2 + h));
+  unpack_bf16x16(t, x);
 }
 
-// stg / stg2 != nullptr: bf16 results go to the warp's staging tiles (TMA-store path) instead of global.
-template <int EPI, bool OUT_F32>
-__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const uint32_t* acc, const float* sbias,
-                                               const uint4* auxr, long long row, int col0, int ncols,
-                                               uint8_t* stg, uint8_t* stg2, int lane, int chunk_in_group,
-                                               uint32_t seed_lo, uint32_t seed_hi) {
-  float v[EW];
-  const bool full = (ncols == EW) && p.vec_ok;
-  // v = alpha * acc + bias
+// v = epilogue(alpha * acc + bias [, x]) for 16 columns of one row; gq = gelu(.) for M3P_EPI_GELU (v = gelu').
+// x: the chunk's aux values (residual / stashed gelu' / tanh output); e0: row-major element index of the chunk's
+// first element (dropout counter).
+template <int EPI>
+__device__ __forceinline__ void epilogue_math(const GemmKernelParams& p, const uint32_t* acc, const float* sbias,
+                                              const float* x, uint32_t e0, uint32_t seed_lo, uint32_t seed_hi,
+                                              float* v, float* gq) {
 #pragma unroll
   for (int j = 0; j < EW / 4; ++j) {
     const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * j);  // broadcast LDS.128
@@ -115,58 +135,65 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
     v[4 * j + 2] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 2]), b.z);
     v[4 * j + 3] = fmaf(p.alpha, __uint_as_float(acc[4 * j + 3]), b.w);
   }
+  if constexpr (EPI == M3P_EPI_DROP_RES) {
+    if (p.thr16 != 0) {
+      if ((e0 & 1u) == 0) {
+#pragma unroll
+        for (int j = 0; j < EW / 2; ++j) {
+          const uint32_t h = drop_hash((e0 >> 1) + j, seed_lo, seed_hi);
+          v[2 * j] = ((h & 0xffffu) >= p.thr16) ? v[2 * j] * p.drop_scale : 0.f;
+          v[2 * j + 1] = ((h >> 16) >= p.thr16) ? v[2 * j + 1] * p.drop_scale : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < EW; ++j)
+          v[j] = drop_keep(e0 + j, seed_lo, seed_hi, p.thr16) ? v[j] * p.drop_scale : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < EW; ++j) v[j] += x[j];
+  } else if constexpr (EPI == M3P_EPI_DGELU) {
+#pragma unroll
+    for (int j = 0; j < EW; ++j) v[j] *= x[j];  // x = gelu'(u) stashed by the forward epilogue
+  } else if constexpr (EPI == M3P_EPI_DTANH) {
+#pragma unroll
+    for (int j = 0; j < EW; ++j) v[j] *= (1.0f - x[j] * x[j]);
+  } else if constexpr (EPI == M3P_EPI_TANH) {
+#pragma unroll
+    for (int j = 0; j < EW; ++j) v[j] = tanhf(v[j]);
+  } else if constexpr (EPI == M3P_EPI_GELU) {
+    // gq = gelu(v), v = gelu'(v): one erf / exp evaluation serves both, and the backward (M3P_EPI_DGELU)
+    // becomes a plain multiply by the stashed derivative.
+#pragma unroll
+    for (int j = 0; j < EW; ++j) gelu_and_grad(v[j], gq[j], v[j]);
+  }
+}
 
-  // auxiliary operand (residual / stashed gelu' / tanh output)
+// Direct-to-global epilogue of one chunk: fp32 outputs (plain or atomic accumulate) and the bf16 fallback for
+// operands whose pitches / bases rule out TMA.
+template <int EPI, bool OUT_F32>
+__device__ __forceinline__ void epilogue_chunk_direct(const GemmKernelParams& p, const uint32_t* acc, const float* sbias,
+                                                      long long row, int col0, int ncols, uint32_t seed_lo,
+                                                      uint32_t seed_hi) {
+  float v[EW], gq[EW], x[EW];
+  const bool full = (ncols == EW) && p.vec_ok;
   if constexpr (epi_has_aux<EPI>()) {
-    float x[EW];
+    const __nv_bfloat16* ap = p.aux + row * p.ldaux + col0;
     if (full) {
-      unpack_bf16x16(auxr, x);
+      uint4 t[2];
+      t[0] = __ldg(reinterpret_cast<const uint4*>(ap));
+      t[1] = __ldg(reinterpret_cast<const uint4*>(ap) + 1);
+      unpack_bf16x16(t, x);
     } else {
-      const __nv_bfloat16* ap = p.aux + row * p.ldaux + col0;
 #pragma unroll
       for (int j = 0; j < EW; ++j) x[j] = (j < ncols) ? __bfloat162float(ap[j]) : 0.f;
     }
-    if constexpr (EPI == M3P_EPI_DROP_RES) {
-      if (p.thr16 != 0) {
-        const uint32_t e0 = static_cast<uint32_t>(row) * static_cast<uint32_t>(p.N) +
-                            static_cast<uint32_t>(col0);
-        if ((e0 & 1u) == 0) {
-#pragma unroll
-          for (int j = 0; j < EW / 2; ++j) {
-            const uint32_t h = drop_hash((e0 >> 1) + j, seed_lo, seed_hi);
-            v[2 * j] = ((h & 0xffffu) >= p.thr16) ? v[2 * j] * p.drop_scale : 0.f;
-            v[2 * j + 1] = ((h >> 16) >= p.thr16) ? v[2 * j + 1] * p.drop_scale : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < EW; ++j)
-            v[j] = drop_keep(e0 + j, seed_lo, seed_hi, p.thr16) ? v[j] * p.drop_scale : 0.f;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < EW; ++j) v[j] += x[j];
-    } else if constexpr (EPI == M3P_EPI_DGELU) {
-#pragma unroll
-      for (int j = 0; j < EW; ++j) v[j] *= x[j];  // x = gelu'(u) stashed by the forward epilogue
-    } else {  // DTANH
-#pragma unroll
-      for (int j = 0; j < EW; ++j) v[j] *= (1.0f - x[j] * x[j]);
-    }
   }
-  if constexpr (EPI == M3P_EPI_TANH) {
-#pragma unroll
-    for (int j = 0; j < EW; ++j) v[j] = tanhf(v[j]);
-  }
+  const uint32_t e0 = static_cast<uint32_t>(row) * static_cast<uint32_t>(p.N) + static_cast<uint32_t>(col0);
+  epilogue_math<EPI>(p, acc, sbias, x, e0, seed_lo, seed_hi, v, gq);
   if constexpr (EPI == M3P_EPI_GELU) {
-    // out2 = gelu(v), out = gelu'(v): one erf / exp evaluation serves both, and the backward
-    // (M3P_EPI_DGELU) becomes a plain multiply by the stashed derivative.
-    float gq[EW];
-#pragma unroll
-    for (int j = 0; j < EW; ++j) gelu_and_grad(v[j], gq[j], v[j]);
     __nv_bfloat16* gp = p.out2 + row * p.ldo2 + col0;
-    if (stg2 != nullptr) {
-      stage_bf16x16(stg2, lane, chunk_in_group, gq);
-    } else if (full) {
+    if (full) {
       store_bf16x16(gp, gq);
     } else {
 #pragma unroll
@@ -174,8 +201,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
         if (j < ncols) gp[j] = __float2bfloat16_rn(gq[j]);
     }
   }
-
-  // ---- stores ----
   if constexpr (OUT_F32) {
     float* op = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
     if (full) {
@@ -200,9 +225,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
     }
   } else {
     __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
-    if (stg != nullptr) {
-      stage_bf16x16(stg, lane, chunk_in_group, v);
-    } else if (full) {
+    if (full) {
       store_bf16x16(op, v);
     } else {
 #pragma unroll
@@ -223,21 +246,25 @@ struct GemmCfg {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
   static constexpr uint32_t BIAS_BYTES = EPI_WARPS * (BN / 2) * 4;
-  // output staging for the TMA-store epilogue: one [32 rows][64 cols] bf16 tile per warp per output
+  // Staging for the TMA epilogue: per epilogue warp a ring of [32 rows][32 cols] bf16 tiles per output.  Epilogues
+  // with an aux operand TMA-LOAD the aux tile into the ring slot two groups ahead, overwrite it in place with the
+  // result and TMA-STORE it (ring of 3); the others only store (ring of 2).
   static constexpr int N_OUT = OUT_F32 ? 0 : (EPI == M3P_EPI_GELU ? 2 : 1);
-  static constexpr uint32_t STG_TILE = 32 * 128;
-  static constexpr uint32_t STG_BYTES = EPI_WARPS * N_OUT * STG_TILE;
-  static constexpr uint32_t BUDGET = 200 * 1024;
+  static constexpr int RING = epi_has_aux<EPI>() ? 3 : 2;
+  static constexpr uint32_t WARP_STG = N_OUT * RING * STG_TILE;
+  static constexpr uint32_t STG_BYTES = EPI_WARPS * WARP_STG;
+  static constexpr uint32_t BAR_BYTES = 512;
+  static constexpr uint32_t BUDGET = 220 * 1024;
   static constexpr int STAGES_FIT = (BUDGET - STG_BYTES - BIAS_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BIAS_BYTES + 1024 /*align*/ + BAR_BYTES;
 };
 
 template <int BN, int EPI, bool OUT_F32, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
-            const GemmKernelParams p) {
+            const __grid_constant__ CUtensorMap tmap_aux, const GemmKernelParams p) {
   using Cfg = GemmCfg<BN, CTA2, EPI, OUT_F32>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NCTA = CTA2 ? 2 : 1;
@@ -251,7 +278,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* aux_bar = tmem_empty + 2;  // [EPI_WARPS][3]: aux tile of a ring slot has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS * 3);
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -267,6 +295,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (p.tma_store) {
       prefetch_tmap(&tmap_o);
       if constexpr (EPI == M3P_EPI_GELU) prefetch_tmap(&tmap_o2);
+      if constexpr (epi_has_aux<EPI>()) prefetch_tmap(&tmap_aux);
     }
   }
   if (warp_idx == 1 && elect_one()) {
@@ -278,6 +307,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], EPI_WARPS * NCTA);  // one arrival per epilogue warp of every CTA of the pair
     }
+    for (int i = 0; i < EPI_WARPS * 3; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -297,9 +327,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp_idx == 0) {
     // ===================== TMA producer (every CTA stages its own halves) =====================
     if (elect_one()) {
+      GT_DECL
       int stage = 0;
       uint32_t phase = 0;
       for (int u = unit0; u < p.num_units; u += unit_stride) {
+        GT_MARK();  // producer: tile start
         int m_tile, n_tile, ks;
         decode_unit(p, u, m_tile, n_tile, ks);
         const int m0 = (m_tile * NCTA + (int)cta_rank) * BLOCK_M;
@@ -331,11 +363,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        GT_MARK();  // producer: last k-block of the tile issued
       }
+      GT_DUMP("prod");
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (the leader CTA's elected thread) =====================
     if (leader && elect_one()) {
+      GT_DECL
       int stage = 0;
       uint32_t phase = 0;
       int acc_stage = 0;
@@ -348,8 +383,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         decode_unit(p, u, m_tile, n_tile, ks);
         const int kb0 = ks * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
+        GT_MARK();  // mma: tile start
         mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
         tc_fence_after();
+        GT_MARK();  // mma: accumulator stage free
         const uint32_t d_tmem = tmem_base + acc_stage * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -373,25 +410,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // accumulator complete (each CTA drains its own 128 rows)
         if constexpr (CTA2) umma_commit_2sm(&tmem_full[acc_stage], 3);
         else umma_commit(&tmem_full[acc_stage]);
+        GT_MARK();  // mma: all MMAs of the tile issued
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
+      GT_DUMP("mma ");
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
-    const int q = warp_idx & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp_idx - 4) >> 2;  // which half of the tile's columns this warp drains
-    constexpr int NCH = BN / 2 / EW;       // chunks per warp
+    const int ew = warp_idx - 4;
+    const int q = warp_idx & 3;   // TMEM lane quarter this warp may access
+    const int half = ew >> 2;     // which half of the tile's columns this warp drains
+    constexpr int NCH = BN / 2 / EW;  // 16-column chunks per warp per tile
+    constexpr int NG = BN / 2 / GW;   // 32-column staging groups per warp per tile
+    constexpr bool HAS_AUX = epi_has_aux<EPI>();
+    constexpr int RING = Cfg::RING;
     const int cbase = half * (BN / 2);
-    float* sbias = bias_smem + (warp_idx - 4) * (BN / 2);
+    float* sbias = bias_smem + ew * (BN / 2);
+    uint8_t* ring = stg_smem + ew * Cfg::WARP_STG;  // slot b, output o at ring + (b * N_OUT + o) * STG_TILE
+    uint64_t* my_aux_bar = aux_bar + ew * 3;
+    const bool use_tma = (!OUT_F32) && p.tma_store;
     uint32_t seed_lo = p.seed_lo, seed_hi = p.seed_hi;
     if constexpr (EPI == M3P_EPI_DROP_RES) mix_seed(p.seed_mix, seed_lo, seed_hi);
+
+    // Staging groups are numbered gg = 0, 1, ... over ALL tiles of this warp (NG per tile); the static tile
+    // schedule makes the coordinates of any future group a pure function of gg, so the aux tile of group gg + 2
+    // (possibly the next tile's) can be requested while group gg + 1 is being computed.
+    auto group_coords = [&](int gg, int& col0, int& row0) -> bool {
+      const long long u = unit0 + static_cast<long long>(gg / NG) * unit_stride;
+      if (u >= p.num_units) return false;
+      int m_tile, n_tile, ks;
+      decode_unit(p, static_cast<int>(u), m_tile, n_tile, ks);
+      col0 = n_tile * BN + cbase + (gg % NG) * GW;
+      row0 = (m_tile * NCTA + (int)cta_rank) * BLOCK_M + q * 32;
+      return col0 < p.N && row0 < p.M;  // a box entirely outside the tensor is neither loaded nor stored
+    };
+    auto issue_aux = [&](int gg) {  // lane 0
+      int col0, row0;
+      if (group_coords(gg, col0, row0)) {
+        const int b = gg % RING;
+        mbar_arrive_expect_tx(&my_aux_bar[b], STG_TILE);
+        tma_load_2d(ring + b * STG_TILE, &tmap_aux, &my_aux_bar[b], col0, row0);
+      }
+    };
+    if constexpr (HAS_AUX) {
+      if (use_tma && lane == 0) { issue_aux(0); issue_aux(1); }
+    }
+    uint32_t aux_phase = 0;  // bit b: parity the next wait on ring slot b expects
+    int gg = 0;
     int acc_stage = 0;
     uint32_t acc_phase = 0;
+    GT_DECL
     for (int u = unit0; u < p.num_units; u += unit_stride) {
+      GT_MARK();  // epi: tile start
       int m_tile, n_tile, ks;
       decode_unit(p, u, m_tile, n_tile, ks);
       const int n0 = n_tile * BN;
-      const long long row = static_cast<long long>(m_tile * NCTA + (int)cta_rank) * BLOCK_M + q * 32 + lane;
+      const int row0 = (m_tile * NCTA + (int)cta_rank) * BLOCK_M + q * 32;  // first row of this warp's sub-tile
+      const long long row = static_cast<long long>(row0) + lane;
       const bool row_ok = row < p.M;
       // stage this warp's bias slice (the global loads overlap the wait for the accumulator)
       for (int c = lane * 4; c < BN / 2; c += 128) {
@@ -409,72 +484,85 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         *reinterpret_cast<float4*>(sbias + c) = b;
       }
-      // the whole aux slice of this thread's row (residual / stashed gelu'), likewise ahead of the
-      // accumulator: its latency hides behind the tile's main loop
-      constexpr bool HAS_AUX = epi_has_aux<EPI>();
-      constexpr int NAUX = HAS_AUX ? NCH : 1;
-      uint4 auxr[NAUX][2];
-      if constexpr (HAS_AUX) {
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-          if (row_ok && p.vec_ok && (n0 + cbase + i * EW + EW <= p.N)) {
-            const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + row * p.ldaux + n0 + cbase + i * EW);
-            auxr[i][0] = __ldg(a4);
-            auxr[i][1] = __ldg(a4 + 1);
-          }
-        }
-      }
       __syncwarp();
+      GT_MARK();  // epi: bias staged
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
+      GT_MARK();  // epi: accumulator ready
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_stage * BN;
-      const bool use_tma = (!OUT_F32) && p.tma_store;
-      uint8_t* stg = use_tma ? stg_smem + (warp_idx - 4) * Cfg::N_OUT * Cfg::STG_TILE : nullptr;
-      uint8_t* stg2 = (use_tma && EPI == M3P_EPI_GELU) ? stg + Cfg::STG_TILE : nullptr;
-      const int row0 = (m_tile * NCTA + (int)cta_rank) * BLOCK_M + q * 32;  // first row of this warp's sub-tile
-      // software-pipelined drain: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed;
-      // every 4 chunks (64 columns) the warp's staging tile leaves through one TMA store
+      // software-pipelined drain: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed
       uint32_t acc[2][EW];
       tmem_ld_32x32b_x16(t_base + cbase, acc[0]);
-      auto chunk = [&](int i, int ii, const uint4* ax) {
-        tmem_ld_wait16(acc[ii]);
-        if (i + 1 < NCH) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
-        const int col0 = n0 + cbase + i * EW;
-        if (use_tma) {
-          if ((i & 3) == 0) {  // staging tile must have been read by the previous group's TMA store
-            if (lane == 0) tma_store_wait_read<0>();
+      if (use_tma) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g, ++gg) {
+          const int b = gg % RING;
+          const int gcol0 = n0 + cbase + g * GW;
+          const bool valid = gcol0 < p.N && row0 < p.M;
+          uint8_t* slot = ring + b * Cfg::N_OUT * STG_TILE;
+          if constexpr (HAS_AUX) {
+            if (valid) {  // this group's aux tile (requested two groups ago) must have landed in the slot
+              mbar_wait(&my_aux_bar[b], (aux_phase >> b) & 1u);
+              aux_phase ^= 1u << b;
+            }
+#ifdef M3P_GEMM_TRACE
+            if (gg >= NG && gg < 2 * NG) GT_MARK();  // epi (2nd tile): aux landed
+#endif
+          } else {
+            if (lane == 0) tma_store_wait_read<RING - 1>();  // the slot's previous store (group gg - RING) was read
             __syncwarp();
           }
-          // rows / columns outside the problem are clipped by the TMA store; skip their math (and aux reads)
-          if (row_ok && col0 < p.N)
-            epilogue_chunk<EPI, OUT_F32>(p, acc[ii], sbias + i * EW, ax, row, col0, min(EW, p.N - col0), stg, stg2,
-                                         lane, i & 3, seed_lo, seed_hi);
-          if ((i & 3) == 3) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0 && col0 - 3 * EW < p.N && row0 < p.M) {
-              tma_store_2d(&tmap_o, stg, col0 - 3 * EW, row0);
-              if constexpr (EPI == M3P_EPI_GELU) tma_store_2d(&tmap_o2, stg2, col0 - 3 * EW, row0);
-              tma_store_commit();
+#pragma unroll
+          for (int ci = 0; ci < GW / EW; ++ci) {
+            const int i = g * (GW / EW) + ci, ii = i & 1;
+            tmem_ld_wait16(acc[ii]);
+            if (i + 1 < NCH) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
+            float v[EW], gq[EW], x[EW];
+            if constexpr (HAS_AUX) unstage_bf16x16(slot, lane, ci, x);
+            const uint32_t e0 = static_cast<uint32_t>(row) * static_cast<uint32_t>(p.N) +
+                                static_cast<uint32_t>(gcol0 + ci * EW);
+            epilogue_math<EPI>(p, acc[ii], sbias + i * EW, x, e0, seed_lo, seed_hi, v, gq);
+            stage_bf16x16(slot, lane, ci, v);  // in place over the aux values this thread just consumed
+            if constexpr (EPI == M3P_EPI_GELU) stage_bf16x16(slot + STG_TILE, lane, ci, gq);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+#ifdef M3P_GEMM_TRACE
+          if (gg >= NG && gg < 2 * NG) GT_MARK();  // epi (2nd tile): group computed and staged
+#endif
+          if (lane == 0) {
+            if (valid) {
+              tma_store_2d(&tmap_o, slot, gcol0, row0);  // rows / columns past the problem are clipped
+              if constexpr (EPI == M3P_EPI_GELU) tma_store_2d(&tmap_o2, slot + STG_TILE, gcol0, row0);
+            }
+            tma_store_commit();  // one bulk group per staging group, valid or not: keeps the wait counts uniform
+            if constexpr (HAS_AUX) {
+              tma_store_wait_read<1>();  // every store but the one just issued has been read: slot (gg + 2) % 3 is free
+              issue_aux(gg + 2);
             }
           }
-        } else if (row_ok && col0 < p.N) {
-          epilogue_chunk<EPI, OUT_F32>(p, acc[ii], sbias + i * EW, ax, row, col0, min(EW, p.N - col0), nullptr,
-                                       nullptr, lane, 0, seed_lo, seed_hi);
+#ifdef M3P_GEMM_TRACE
+          if (gg >= NG && gg < 2 * NG) GT_MARK();  // epi (2nd tile): store issued, next aux requested
+#endif
         }
-      };
-      if constexpr (HAS_AUX) {
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) chunk(i, i & 1, auxr[i]);
       } else {
 #pragma unroll 1
         for (int i0 = 0; i0 < NCH; i0 += 2) {
-          chunk(i0, 0, auxr[0]);
-          chunk(i0 + 1, 1, auxr[0]);
+#pragma unroll
+          for (int ii = 0; ii < 2; ++ii) {
+            const int i = i0 + ii;
+            tmem_ld_wait16(acc[ii]);
+            if (i + 1 < NCH) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
+            const int col0 = n0 + cbase + i * EW;
+            if (row_ok && col0 < p.N)
+              epilogue_chunk_direct<EPI, OUT_F32>(p, acc[ii], sbias + i * EW, row, col0, min(EW, p.N - col0), seed_lo,
+                                                  seed_hi);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
+      GT_MARK();  // epi: tile drained
       if (lane == 0) {
         if constexpr (CTA2) mbar_arrive_cluster(&tmem_empty[acc_stage], 0);  // the leader's MMA thread waits on it
         else mbar_arrive(&tmem_empty[acc_stage]);
@@ -482,6 +570,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait<0>();  // smem must outlive the bulk stores that read it
+#ifdef M3P_GEMM_TRACE
+    if (warp_idx == 4 && lane == 0) { GT_MARK(); GT_DUMP("epi "); }
+#endif
   }
 
   tc_fence_before();
@@ -497,7 +588,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 template <int BN, int EPI, bool OUT_F32, bool CTA2>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
-                       const GemmKernelParams& p, cudaStream_t stream) {
+                       const CUtensorMap& tx, const GemmKernelParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTA2, EPI, OUT_F32>;
   auto kfn = gemm_kernel<BN, EPI, OUT_F32, CTA2>;
   static bool attr_set = false;  // per instantiation
@@ -523,27 +614,27 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  M3P_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, ta, tb, to, to2, p));
+  M3P_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, ta, tb, to, to2, tx, p));
   return M3P_OK;
 }
 
 template <int BN, bool CTA2>
 static int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
-                        const GemmKernelParams& p, int epi, bool out_f32, cudaStream_t s) {
+                        const CUtensorMap& tx, const GemmKernelParams& p, int epi, bool out_f32, cudaStream_t s) {
   if (out_f32) {
     if (epi != M3P_EPI_LINEAR) {
       set_last_error("m3p_gemm_bf16: fp32 output only with M3P_EPI_LINEAR");
       return M3P_ERR_UNSUPPORTED;
     }
-    return launch_gemm<BN, M3P_EPI_LINEAR, true, CTA2>(ta, tb, to, to2, p, s);
+    return launch_gemm<BN, M3P_EPI_LINEAR, true, CTA2>(ta, tb, to, to2, tx, p, s);
   }
   switch (epi) {
-    case M3P_EPI_LINEAR: return launch_gemm<BN, M3P_EPI_LINEAR, false, CTA2>(ta, tb, to, to2, p, s);
-    case M3P_EPI_GELU: return launch_gemm<BN, M3P_EPI_GELU, false, CTA2>(ta, tb, to, to2, p, s);
-    case M3P_EPI_DROP_RES: return launch_gemm<BN, M3P_EPI_DROP_RES, false, CTA2>(ta, tb, to, to2, p, s);
-    case M3P_EPI_DGELU: return launch_gemm<BN, M3P_EPI_DGELU, false, CTA2>(ta, tb, to, to2, p, s);
-    case M3P_EPI_TANH: return launch_gemm<BN, M3P_EPI_TANH, false, CTA2>(ta, tb, to, to2, p, s);
-    case M3P_EPI_DTANH: return launch_gemm<BN, M3P_EPI_DTANH, false, CTA2>(ta, tb, to, to2, p, s);
+    case M3P_EPI_LINEAR: return launch_gemm<BN, M3P_EPI_LINEAR, false, CTA2>(ta, tb, to, to2, tx, p, s);
+    case M3P_EPI_GELU: return launch_gemm<BN, M3P_EPI_GELU, false, CTA2>(ta, tb, to, to2, tx, p, s);
+    case M3P_EPI_DROP_RES: return launch_gemm<BN, M3P_EPI_DROP_RES, false, CTA2>(ta, tb, to, to2, tx, p, s);
+    case M3P_EPI_DGELU: return launch_gemm<BN, M3P_EPI_DGELU, false, CTA2>(ta, tb, to, to2, tx, p, s);
+    case M3P_EPI_TANH: return launch_gemm<BN, M3P_EPI_TANH, false, CTA2>(ta, tb, to, to2, tx, p, s);
+    case M3P_EPI_DTANH: return launch_gemm<BN, M3P_EPI_DTANH, false, CTA2>(ta, tb, to, to2, tx, p, s);
     default:
       set_last_error("m3p_gemm_bf16: unknown epilogue %d", epi);
       return M3P_ERR_INVALID_ARGUMENT;
@@ -652,23 +743,27 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   else         rc = get_tmap_2d_bf16(&tb, a->b, (uint64_t)a->n, (uint64_t)a->k, (uint64_t)a->ldb, 64, BLOCK_K);
   if (rc) return rc;
 
-  // bf16 outputs: [32 rows][64 cols] boxes for the TMA-store epilogue
-  CUtensorMap to = ta, to2 = ta;
+  // bf16 outputs (and the aux operand): [32 rows][32 cols] SWIZZLE_64B boxes for the TMA epilogue
+  CUtensorMap to = ta, to2 = ta, tx = ta;
   p.tma_store = (!a->out_f32 && p.vec_ok && use_tma_store()) ? 1 : 0;
   if (p.tma_store) {
-    rc = get_tmap_2d_bf16(&to, a->out, (uint64_t)a->n, (uint64_t)a->m, (uint64_t)a->ldo, 64, 32);
+    rc = get_tmap_2d_bf16(&to, a->out, (uint64_t)a->n, (uint64_t)a->m, (uint64_t)a->ldo, GW, 32);
     if (rc) return rc;
     if (a->epilogue == M3P_EPI_GELU) {
-      rc = get_tmap_2d_bf16(&to2, a->out2, (uint64_t)a->n, (uint64_t)a->m, (uint64_t)a->ldo2, 64, 32);
+      rc = get_tmap_2d_bf16(&to2, a->out2, (uint64_t)a->n, (uint64_t)a->m, (uint64_t)a->ldo2, GW, 32);
+      if (rc) return rc;
+    }
+    if (a->aux != nullptr) {
+      rc = get_tmap_2d_bf16(&tx, a->aux, (uint64_t)a->n, (uint64_t)a->m, (uint64_t)a->ldaux, GW, 32);
       if (rc) return rc;
     }
   }
   if (cta2) {
-    if (BN == 256) return dispatch_epi<256, true>(ta, tb, to, to2, p, a->epilogue, a->out_f32 != 0, stream);
-    return dispatch_epi<128, true>(ta, tb, to, to2, p, a->epilogue, a->out_f32 != 0, stream);
+    if (BN == 256) return dispatch_epi<256, true>(ta, tb, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
+    return dispatch_epi<128, true>(ta, tb, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
   }
-  if (BN == 256) return dispatch_epi<256, false>(ta, tb, to, to2, p, a->epilogue, a->out_f32 != 0, stream);
-  return dispatch_epi<128, false>(ta, tb, to, to2, p, a->epilogue, a->out_f32 != 0, stream);
+  if (BN == 256) return dispatch_epi<256, false>(ta, tb, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
+  return dispatch_epi<128, false>(ta, tb, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
 }
 
 }  // namespace m3p

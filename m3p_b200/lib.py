@@ -92,6 +92,8 @@ PROTOTYPES = {
     "m3p_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                           c_int64, c_float, c_void_p],
     "m3p_layernorm_bwd": [POINTER(LnBwdArgs), c_void_p],
+    "m3p_layernorm_bwd_rows": [POINTER(LnBwdArgs), c_void_p],
+    "m3p_layernorm_bwd_cols": [POINTER(LnBwdArgs), c_void_p],
     "m3p_colsum_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p],
     "m3p_cast_f32_bf16": [c_void_p, c_void_p, c_int64, c_float, c_void_p],
     "m3p_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],

@@ -29,6 +29,22 @@ def use_current_stream():
     return _STREAM
 
 
+class on_stream:
+    """`with ops.on_stream(torch_stream):` — enqueue the calls inside on another stream (the side stream
+    that carries parameter-gradient kernels underneath the activation-gradient chain)."""
+
+    def __init__(self, stream):
+        self.handle = _vp(stream.cuda_stream)
+
+    def __enter__(self):
+        global _STREAM
+        self.prev, _STREAM = _STREAM, self.handle
+
+    def __exit__(self, *exc):
+        global _STREAM
+        _STREAM = self.prev
+
+
 def _stream():
     global LAUNCHES
     LAUNCHES += 1
@@ -130,7 +146,9 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps, seqlen=None, S=0):
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, *, seqlen=None, S=0, dx_drop=None, dx_drop_p=0.0, dx_seed=0,
-                  dy_drop_p=0.0, dy_seed=0, dgamma=None, dbeta=None, dbias=None):
+                  dy_drop_p=0.0, dy_seed=0, dgamma=None, dbeta=None, dbias=None, phase="both"):
+    """phase: "both" (row pass then column pass), "rows" (dx / dx_drop only) or "cols" (dgamma / dbeta / dbias
+    only, after the row pass of the same arguments has been enqueued)."""
     a = L.LnBwdArgs()
     a.dy, a.x, a.mean, a.rstd, a.gamma = dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr()
     a.seqlen, a.S = _p(seqlen), S
@@ -141,7 +159,9 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, *, seqlen=None, S=0, dx_drop=Non
     a.x_f32 = int(x.dtype == torch.float32)
     a.dy_f32 = int(dy.dtype == torch.float32)
     a.dx_f32 = int(dx.dtype == torch.float32)
-    L.check(_lib().m3p_layernorm_bwd(_byref(a), _stream()), "m3p_layernorm_bwd")
+    fn = {"both": _lib().m3p_layernorm_bwd, "rows": _lib().m3p_layernorm_bwd_rows,
+          "cols": _lib().m3p_layernorm_bwd_cols}[phase]
+    L.check(fn(_byref(a), _stream()), "m3p_layernorm_bwd")
 
 
 def colsum(x, out, rows=None, n=None, ld=None):

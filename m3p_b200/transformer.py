@@ -21,6 +21,7 @@ Memory layout (HBM):
     reference API are transposed views of them.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -111,6 +112,8 @@ class TransformerModel(nn.Module):
         self._device_checked = False
         self._emb_touched = None      # token-id tensors scattered into _emb_grad since it was last cleared
         self._emb_dense_dirty = True  # True once a dense update (tied MLM head) or foreign writer touched it
+        self.overlap_grads = os.environ.get("M3P_SIDE_STREAM", "1") != "0"
+        self._side_streams = {}
         self._build_parameters()
 
     # ------------------------------------------------------------------------------------------
@@ -399,6 +402,12 @@ class TransformerModel(nn.Module):
         L.load().m3p_set_seed_mix(word.data_ptr())
         return self._seed_base, word
 
+    def _side_stream_for(self, dev):
+        key = (dev.type, dev.index)
+        if key not in self._side_streams:
+            self._side_streams[key] = torch.cuda.Stream(device=dev)
+        return self._side_streams[key]
+
     def _require_cuda(self, t):
         if not t.is_cuda:
             raise L.M3PError("m3p_b200 runs on a B200 only: got a %s tensor (there is no CPU fallback; "
@@ -635,47 +644,57 @@ class TransformerModel(nn.Module):
         hook = self._grad_ready_hook
         if hook is not None:
             hook("heads", *self._segments["heads"])  # head backward ran before the encoder's
+        # The activation-gradient chain (LN rows -> dgrad -> dgrad -> LN rows -> dgrad -> attention -> dgrad) runs on
+        # the current stream; everything that only produces PARAMETER gradients (wgrad GEMMs, LN column pass, bias
+        # column sums) goes to a side stream, so HBM-bound reductions run underneath tensor-bound GEMMs and the
+        # persistent GEMMs of one stream fill the partially-empty last wave of the other's.
+        sq = _SideQueue(self._side_stream_for(dev) if self.overlap_grads else None, hook)
         for i in reversed(range(self.n_layers)):
             w, gr, s = self._layer_views(i), self._layer_grads(i), st["layers"][i]
             # layer_norm2 (+ row mask) and the FFN dropout           (:956-958, :226)
             dx2 = e(M, d)
             dx2d = e(M, d) if p_drop > 0 else None
-            ops.layernorm_bwd(dh, s["x2"], s["mean2"], s["rstd2"], w["g2"], dx2, seqlen=seqlen, S=S, dx_drop=dx2d,
-                              dx_drop_p=p_drop, dx_seed=s["s2"], dgamma=gr["g2"], dbeta=gr["b2"], dbias=gr["bb2"])
-            if dx2d is None:
-                dx2d = dx2
-            # lin2 dgrad fused with gelu'(u); lin2 wgrad                (:224-225)
+            ln2 = dict(seqlen=seqlen, S=S, dx_drop=dx2d, dx_drop_p=p_drop, dx_seed=s["s2"], dgamma=gr["g2"],
+                       dbeta=gr["b2"], dbias=gr["bb2"])
+            ops.layernorm_bwd(dh, s["x2"], s["mean2"], s["rstd2"], w["g2"], dx2, phase="rows", **ln2)
+            dx2d_ = dx2 if dx2d is None else dx2d
+            sq.fork()
+            sq.run(lambda: ops.layernorm_bwd(dh, s["x2"], s["mean2"], s["rstd2"], w["g2"], dx2, phase="cols", **ln2))
+            sq.run(lambda: ops.wgrad(dx2d_, s["g"], gr["w2"]))                  # lin2 wgrad            (:225)
+            # lin2 dgrad fused with gelu'(u)                                   (:224-225)
             du = e(M, 4 * d)
-            ops.dgrad(dx2d, w["w2"], du, epi=L.M3P_EPI_DGELU, aux=s["gp"])
-            ops.wgrad(dx2d, s["g"], gr["w2"])
-            # lin1 dgrad + residual branch; lin1 wgrad / bias           (:223, :956)
+            ops.dgrad(dx2d_, w["w2"], du, epi=L.M3P_EPI_DGELU, aux=s["gp"])
+            sq.fork()
+            sq.run(lambda: ops.colsum(du, gr["bb1"]))
+            sq.run(lambda: ops.wgrad(du, s["h1"], gr["w1"]))                    # lin1 wgrad / bias     (:223)
+            # lin1 dgrad + residual branch                                     (:223, :956)
             dh1 = e(M, d)
             ops.dgrad(du, w["w1"], dh1, epi=L.M3P_EPI_DROP_RES, aux=dx2)
-            ops.wgrad(du, s["h1"], gr["w1"])
-            ops.colsum(du, gr["bb1"])
-            del du
             # layer_norm1 and the attention-output dropout              (:951-953)
             dx1 = e(M, d)
             dx1d = e(M, d) if p_drop > 0 else None
-            ops.layernorm_bwd(dh1, s["x1"], s["mean1"], s["rstd1"], w["g1"], dx1, dx_drop=dx1d, dx_drop_p=p_drop,
-                              dx_seed=s["s1"], dgamma=gr["g1"], dbeta=gr["b1"], dbias=gr["bo"])
-            if dx1d is None:
-                dx1d = dx1
+            ln1 = dict(dx_drop=dx1d, dx_drop_p=p_drop, dx_seed=s["s1"], dgamma=gr["g1"], dbeta=gr["b1"], dbias=gr["bo"])
+            ops.layernorm_bwd(dh1, s["x1"], s["mean1"], s["rstd1"], w["g1"], dx1, phase="rows", **ln1)
+            dx1d_ = dx1 if dx1d is None else dx1d
+            sq.fork()
+            sq.run(lambda: ops.layernorm_bwd(dh1, s["x1"], s["mean1"], s["rstd1"], w["g1"], dx1, phase="cols", **ln1))
+            sq.run(lambda: ops.wgrad(dx1d_, s["ctx"], gr["wo"]))
             dctx = e(M, d)
-            ops.dgrad(dx1d, w["wo"], dctx)
-            ops.wgrad(dx1d, s["ctx"], gr["wo"])
+            ops.dgrad(dx1d_, w["wo"], dctx)
             # attention core                                            (:197-205)
             dqkv = e(M, 3 * d)
             ops.attention_bwd(s["qkv"], seqlen, B, S, H, scale, p_att, s["sa"], s["ctx"], s["lse"], dctx, dqkv)
-            # q/k/v projections                                         (:178-181)
+            sq.fork()
+            sq.run(lambda: ops.colsum(dqkv, gr["bqkv"]))
+            sq.run(lambda: ops.wgrad(dqkv, s["h"], gr["wqkv"]))                 # q/k/v projections     (:178-181)
             dhp = e(M, d)
             ops.dgrad(dqkv, w["wqkv"], dhp, epi=L.M3P_EPI_DROP_RES, aux=dx1)
-            ops.wgrad(dqkv, s["h"], gr["wqkv"])
-            ops.colsum(dqkv, gr["bqkv"])
+            # the side stream may still be reading these: keep them alive until the join one layer later
+            sq.close("layer%d" % i, self._segments["layer%d" % i], (dh, s, dx2, dx2d, du, dh1, dx1, dx1d, dqkv))
             dh = dhp
             st["layers"][i] = None
-            if hook is not None:
-                hook("layer%d" % i, *self._segments["layer%d" % i])
+            del s, du, dx2, dx2d, dh1, dx1, dx1d, dqkv, dctx
+        sq.join_all()
         # ---- embedding stage ----
         spec = st["spec"]
         flags = spec["flags"]
@@ -729,6 +748,53 @@ class TransformerModel(nn.Module):
         if hook is not None:
             hook("embed", *self._segments["embed"])
         return d_ximg, d_text
+
+
+class _SideQueue:
+    """Fork/join bookkeeping for the side stream of `_encode_backward` (works eagerly and under CUDA-graph
+    capture, where the events become graph edges).  `fork()` makes the side stream wait for what the main
+    stream has enqueued so far; `run(fn)` enqueues fn's kernels on the side stream; `close()` marks a group
+    (one layer) and defers its join by one group so the main chain never waits for the side stream's most
+    recent work; `join_all()` makes the main stream wait for everything.  With stream=None everything runs
+    inline on the main stream."""
+
+    def __init__(self, stream, hook):
+        self.side, self.hook = stream, hook
+        self.main = torch.cuda.current_stream() if stream is not None else None
+        self.pending = []
+
+    def fork(self):
+        if self.side is not None:
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            self.side.wait_event(ev)
+
+    def run(self, fn):
+        if self.side is None:
+            fn()
+        else:
+            with ops.on_stream(self.side):
+                fn()
+
+    def _join(self, upto):
+        while len(self.pending) > upto:
+            ev, name, seg, keep = self.pending.pop(0)
+            if ev is not None:
+                self.main.wait_event(ev)
+            del keep
+            if self.hook is not None:
+                self.hook(name, *seg)
+
+    def close(self, name, seg, keep):
+        ev = None
+        if self.side is not None:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.pending.append((ev, name, seg, keep if self.side is not None else None))
+        self._join(1 if self.side is not None else 0)
+
+    def join_all(self):
+        self._join(0)
 
 
 class _EncoderFn(torch.autograd.Function):

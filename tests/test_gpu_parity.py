@@ -165,6 +165,14 @@ def test_layernorm_forward_backward(m3p, d):
     assert _rel(y, ref) < KERNEL_TOL and _rel(dx, x32.grad) < KERNEL_TOL
     assert _rel(dg, g32.grad) < 1e-4 and _rel(db, b32.grad) < 1e-4 and _rel(dbias, x32.grad.sum(0)) < 1e-2
     assert float((y.float() * (1 - mask)).abs().max()) == 0.0
+    # the row pass and the column pass on their own (the column pass runs on a side stream in the backward)
+    dx2 = torch.empty_like(x)
+    dg2, db2, dbias2 = (torch.zeros(d, device="cuda") for _ in range(3))
+    kw = dict(seqlen=seqlen, S=S, dgamma=dg2, dbeta=db2, dbias=dbias2)
+    ops.layernorm_bwd(dy, x, mean, rstd, gam, dx2, phase="rows", **kw)
+    assert float(dg2.abs().max()) == 0.0 and torch.equal(dx2, dx)
+    ops.layernorm_bwd(dy, x, mean, rstd, gam, dx2, phase="cols", **kw)
+    assert _rel(dg2, dg) < 1e-6 and _rel(db2, db) < 1e-6 and _rel(dbias2, dbias) < 1e-6
 
 
 @pytest.mark.parametrize("n,V,ign", [(64, 1600, -1), (33, 1002, -100), (5, 250002, -100)])
@@ -342,6 +350,27 @@ def test_gradient_accumulation_and_zero_grad(m3p):
         p.grad = None  # what torch.optim.Optimizer.zero_grad() does by default
     pretrain_step(model, b, 2)[0].backward()
     assert _rel(model._flat_grad, g1) < 1e-3
+
+
+def test_side_stream_backward_matches_inline(m3p):
+    """The parameter-gradient kernels run on a side stream underneath the activation-gradient chain; the
+    result must equal the single-stream order (same kernels, same inputs; fp32 atomics reorder only)."""
+    from m3p_b200.train_step import pretrain_step, synthetic_batch
+    ns = _ns(768, 3, 12, 3000, dropout=0.1)
+    b = synthetic_batch(8, 24, 10, ns.n_words, sample_n=4, seed=5, ragged=True, n_mask_text=3, n_mask_img=2, device="cuda")
+    grads = []
+    for overlap in (False, True, True):
+        model = _model(m3p, ns)
+        model.overlap_grads = overlap
+        for _ in range(2):
+            model.zero_grad()
+            total, _ = pretrain_step(model, b, 4)
+            total.backward()
+        torch.cuda.synchronize()
+        grads.append((float(total.detach()), model._flat_grad.clone(), model._emb_grad.clone()))
+    for loss, flat, emb in grads[1:]:
+        assert loss == grads[0][0]
+        assert _rel(flat, grads[0][1]) < 1e-5 and _rel(emb, grads[0][2]) < 1e-5
 
 
 def test_dropout_training_step_is_seeded_and_finite(m3p):
