@@ -194,6 +194,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its banner there)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -222,8 +224,12 @@ def main():
         step_keys += ["pred_mask_text", "y_text", "obj_labels", "ori_feats", "mrfr_weight"]
     h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in step_keys)
 
-    use_graph = not args.no_graph and world == 1
-    graphed = GraphedStep(model, resident, CFG["sample_n"], heads, warmup=3) if use_graph else None
+    use_graph = not args.no_graph
+    graphed = None
+    if use_graph:  # for N > 1 the NCCL gradient exchange is captured into the same graph
+        graphed = GraphedStep(model, resident, CFG["sample_n"], heads, warmup=3,
+                              after_backward=reducer.finish if world > 1 else None,
+                              capture_error_mode="thread_local" if world > 1 else "global")
 
     def step(batch):
         if graphed is not None:  # `batch` is None (replay on the static inputs) or a dict of new inputs to copy in
@@ -295,7 +301,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args.heads), "global_batch": B * world, "seq_len": CFG["T"] + CFG["R"],
                        "parallelism": "dp%d" % world, "dropout": CFG["dropout"], "vocab": CFG["n_words"],
-                       "launch": "CUDA graph replay (one capture of zero_grad+fwd+loss+bwd)" if graphed is not None
+                       "launch": "CUDA graph replay (one capture of zero_grad+fwd+loss+bwd%s)" % (" + NCCL gradient exchange" if world > 1 else "") if graphed is not None
                        else "per-kernel launches from Python",
                        "l2": "per-step working set (0.18 GB bf16 weights + >4 GB activations) >> 126 MB L2; no flush needed",
                        "gflop_per_pair": gf},
@@ -326,6 +332,11 @@ def main():
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        if graphed is not None:  # NCCL: graphs holding captured collectives must go before the communicator does
+            graphed.release()
+        del graphed
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

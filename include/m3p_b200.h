@@ -297,6 +297,32 @@ M3P_API int m3p_embed_bwd_route(const m3p_embed_bwd_args* args, m3p_stream_t str
 M3P_API int m3p_loc_wgrad(const void* de, const float* image_loc, float* dw_loc, int64_t B, int64_t R, int64_t d,
                           m3p_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step: Trainer.optimize (xtrainer.py:205-243) = clip_grad_norm_ over all
+ * parameters + optim.Adam.step (optim.py:45-86), on the flat fp32 parameter / gradient buffers.
+ * m3p_sumsq_f32: *out += sum_i x[i]^2 (one device scalar; call once per gradient buffer, zero it first).
+ * m3p_adam_step, per element (grad_sumsq read on the device, no host sync):
+ *   g' = g * min(1, max_grad_norm / (sqrt(*grad_sumsq) + 1e-6))        (skipped when grad_sumsq == NULL
+ *                                                                       or max_grad_norm <= 0)
+ *   m = beta1 m + (1-beta1) g' ; v = beta2 v + (1-beta2) g'^2 ; p -= weight_decay*lr*p ;
+ *   p -= lr * sqrt(1-beta2^step)/(1-beta1^step) * m / (sqrt(v) + eps)
+ *   param_bf16[i] = bf16(p) when given (the tensor-core operand copy); grad[i] = 0 when zero_grad. */
+M3P_API int m3p_sumsq_f32(const float* x, int64_t n, float* out, m3p_stream_t stream);
+typedef struct m3p_adam_args {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  void* param_bf16; /* optional */
+  int64_t n;
+  int64_t step; /* 1-based update count (optim.py:68) */
+  float lr, beta1, beta2, eps, weight_decay;
+  const float* grad_sumsq; /* optional device scalar */
+  float max_grad_norm;
+  int32_t zero_grad;
+} m3p_adam_args;
+M3P_API int m3p_adam_step(const m3p_adam_args* args, m3p_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ class GradReducer:
         self._works = []
         self._done = set()
         self._post = []
+        self._gather = {}  # persistent (all_ids, all_rows) buffers of the row-sparse exchange, keyed by size
         self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"  # gloo has no AVG: SUM then scale
         model._grad_ready_hook = self._segment_ready if self.world > 1 else None
 
@@ -55,8 +56,13 @@ class GradReducer:
         cnt = torch.zeros(g.shape[0], dtype=torch.float32, device=g.device)
         cnt.index_add_(0, ids, torch.ones(ids.numel(), dtype=torch.float32, device=g.device))
         rows = g.index_select(0, ids) / (cnt.index_select(0, ids) * self.world).unsqueeze(1)
-        all_ids = torch.empty(self.world * ids.numel(), dtype=ids.dtype, device=ids.device)
-        all_rows = torch.empty(self.world * ids.numel(), g.shape[1], dtype=g.dtype, device=g.device)
+        # persistent receive buffers: the NEXT step's zero_grad clears the rows listed in all_ids, so under CUDA-graph
+        # replay (and across eager steps) that tensor must stay where it is
+        key = (self.world * ids.numel(), g.shape[1], g.dtype, ids.device)
+        if key not in self._gather:
+            self._gather[key] = (torch.empty(key[0], dtype=ids.dtype, device=ids.device),
+                                 torch.empty(key[0], key[1], dtype=g.dtype, device=g.device))
+        all_ids, all_rows = self._gather[key]
         dist.all_gather_into_tensor(all_ids, ids, group=self.group)
         dist.all_gather_into_tensor(all_rows, rows, group=self.group)
         g.index_fill_(0, ids, 0.0)

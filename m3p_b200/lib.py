@@ -80,6 +80,16 @@ class EmbedBwdArgs(ctypes.Structure):
     ]
 
 
+class AdamArgs(ctypes.Structure):
+    _fields_ = [
+        ("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+        ("param_bf16", c_void_p),
+        ("n", c_int64), ("step", c_int64),
+        ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("weight_decay", c_float),
+        ("grad_sumsq", c_void_p), ("max_grad_norm", c_float), ("zero_grad", c_int32),
+    ]
+
+
 # name -> argtypes (all return int).  Must list every M3P_API symbol of include/m3p_b200.h
 # (tests/test_abi.py checks this table against the header).
 PROTOTYPES = {
@@ -111,6 +121,8 @@ PROTOTYPES = {
     "m3p_embed_fwd": [POINTER(EmbedArgs), c_void_p],
     "m3p_embed_bwd_route": [POINTER(EmbedBwdArgs), c_void_p],
     "m3p_loc_wgrad": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
+    "m3p_sumsq_f32": [c_void_p, c_int64, c_void_p, c_void_p],
+    "m3p_adam_step": [POINTER(AdamArgs), c_void_p],
 }
 
 _lib = None

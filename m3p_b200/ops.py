@@ -235,3 +235,19 @@ def embed_bwd_route(args):
 def loc_wgrad(de, image_loc, dw_loc, B, R, d):
     L.check(_lib().m3p_loc_wgrad(de.data_ptr(), image_loc.data_ptr(), dw_loc.data_ptr(), B, R, d, _stream()),
             "m3p_loc_wgrad")
+
+
+def sumsq(x, out):
+    """out[0] += sum(x^2) (fp32, 16-byte aligned buffer)."""
+    L.check(_lib().m3p_sumsq_f32(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "m3p_sumsq_f32")
+
+
+def adam_step(p, g, m, v, step, lr, beta1, beta2, eps, weight_decay=0.0, p16=None, grad_sumsq=None, max_grad_norm=0.0,
+              zero_grad=False):
+    a = L.AdamArgs()
+    a.param, a.grad, a.exp_avg, a.exp_avg_sq = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+    a.param_bf16 = _p(p16)
+    a.n, a.step = p.numel(), step
+    a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = lr, beta1, beta2, eps, weight_decay
+    a.grad_sumsq, a.max_grad_norm, a.zero_grad = _p(grad_sumsq), max_grad_norm, int(zero_grad)
+    L.check(_lib().m3p_adam_step(_byref(a), _stream()), "m3p_adam_step")

@@ -123,9 +123,12 @@ class GraphedStep:
     host memory is asynchronous).  Dropout stays fresh across replays because the seeds live in a device word
     bumped inside the graph (TransformerModel._next_seed)."""
 
-    def __init__(self, model, batch, sample_n=4, heads=("rel",), lambdas=None, warmup=3, after_backward=None):
+    def __init__(self, model, batch, sample_n=4, heads=("rel",), lambdas=None, warmup=3, after_backward=None,
+                 capture_error_mode="global"):
         self.model, self.batch = model, {k: v.clone() for k, v in batch.items()}
         self.sample_n, self.heads, self.lambdas, self.after_backward = sample_n, heads, lambdas, after_backward
+        model.invalidate_operands()  # the captured step always re-casts the operands and clears the gradients:
+        model._grads_clean = False   # what the graph contains must not depend on what an optimizer did before
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up off the default stream: allocations, kernel attributes, scratch
@@ -136,7 +139,9 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         from . import ops
         n0 = ops.LAUNCHES
-        with torch.cuda.graph(self.graph):
+        # after_backward may enqueue NCCL collectives (ddp.GradReducer.finish): they are captured like any other
+        # kernel; pass capture_error_mode="thread_local" then, so NCCL's watchdog thread may keep polling events
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.loss = self._eager()
         self.launches_per_step = ops.LAUNCHES - n0
 
@@ -147,6 +152,12 @@ class GraphedStep:
         if self.after_backward is not None:
             self.after_backward()
         return total.detach()
+
+    def release(self):
+        """Drop the captured graph (needed before torch.distributed.destroy_process_group() when collectives
+        were captured: NCCL requires graphs that hold its kernels to be destroyed before the communicator)."""
+        self.graph.reset()
+        self.graph = None
 
     def step(self, new_batch=None):
         if new_batch is not None:

@@ -114,7 +114,14 @@ class TransformerModel(nn.Module):
         self._emb_dense_dirty = True  # True once a dense update (tied MLM head) or foreign writer touched it
         self.overlap_grads = os.environ.get("M3P_SIDE_STREAM", "1") != "0"
         self._side_streams = {}
+        # set by m3p_b200.optim after a fused step (which also writes the bf16 operand copies and zeroes the
+        # gradients): lets refresh_operands() / zero_grad() skip work that has already been done
+        self._operands_valid = False
+        self._emb16_valid = False
+        self._grads_clean = False
         self._build_parameters()
+        from .optim import tag_parameters
+        tag_parameters(self)
 
     # ------------------------------------------------------------------------------------------
     # parameters
@@ -282,6 +289,18 @@ class TransformerModel(nn.Module):
         self._emb_grad = None
         self._proj_grad = None
         self._emb_touched, self._emb_dense_dirty = None, True
+        self.invalidate_operands()
+        self._grads_clean = False
+
+    def invalidate_operands(self):
+        """Call after editing parameters by hand: the next forward re-casts the bf16 operand copies."""
+        self._operands_valid = False
+        self._emb16_valid = False
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_operands()
+        return out
 
     # -- views ------------------------------------------------------------------------------------
     def _w32(self, name):
@@ -310,10 +329,11 @@ class TransformerModel(nn.Module):
     def refresh_operands(self, embeddings=False):
         """bf16 tensor-core copies of the fp32 masters (one cast kernel over the flat buffer)."""
         ops.use_current_stream()
-        if self._flat16 is None:
-            self._flat16 = torch.empty(self._flat_numel, dtype=_BF16, device=self._flat.device)
-        ops.cast_f32_bf16(self._flat, self._flat16, self._flat_numel)
-        if embeddings:
+        if self._flat16 is None or not self._operands_valid:
+            if self._flat16 is None:
+                self._flat16 = torch.empty(self._flat_numel, dtype=_BF16, device=self._flat.device)
+            ops.cast_f32_bf16(self._flat, self._flat16, self._flat_numel)
+        if embeddings and (self._emb16 is None or not self._emb16_valid):
             if self._emb16 is None:
                 self._emb16 = torch.empty(self._proj.shape, dtype=_BF16, device=self._flat.device)
             ops.cast_f32_bf16(self._proj.data, self._emb16, self._proj.numel())
@@ -340,11 +360,12 @@ class TransformerModel(nn.Module):
             detached = True
             self._proj.grad = self._proj_grad
         # zero_grad(set_to_none=True) dropped the views: the buffers still hold the last step's sums
-        if (detached and not fresh) or zero:
+        if ((detached and not fresh) or zero) and not self._grads_clean:
             self._flat_grad.zero_()
             self._zero_emb_grad()
             if self._proj_grad is not None and self._proj_grad is not self._emb_grad:
                 self._proj_grad.zero_()
+        self._grads_clean = bool(zero or fresh)  # False once a backward is about to accumulate
 
     def _zero_emb_grad(self):
         """The token-embedding gradient is 68 % of all gradient bytes (V x d fp32) but, without the MLM head,

@@ -218,6 +218,34 @@ def pretrain_step_losses(sd, n_layers, n_heads, batch, sample_n, heads=("mlm", "
 
 # ---- synthetic batches (imitates retrieval_pretrain_collate xtrainer.py:960-1045) ----
 
+def clip_coef(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_ as the trainer calls it (xtrainer.py:222-225): one global L2 norm over all
+    gradients, coefficient max_norm / (norm + 1e-6) clamped to 1.  Returns (coef, total_norm)."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return coef, total
+
+
+def adam_step(p, g, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """optim.py:45-86, one parameter tensor, in place; `step` is the 1-based update count (:68)."""
+    b1, b2 = betas
+    exp_avg.mul_(b1).add_(g, alpha=1 - b1)                       # :72
+    exp_avg_sq.mul_(b2).addcmul_(g, g, value=1 - b2)             # :73
+    denom = exp_avg_sq.sqrt().add_(eps)                          # :74
+    step_size = lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step)  # :76-78
+    if weight_decay != 0:
+        p.add_(p, alpha=-weight_decay * lr)                      # :80-81
+    p.addcdiv_(exp_avg, denom, value=-step_size)                 # :83
+    return p
+
+
+def lr_inverse_sqrt(num_updates, lr, warmup_updates=4000, warmup_init_lr=1e-7, exp_factor=0.5):
+    """AdamInverseSqrtWithWarmup.get_lr_for_step — optim.py:129-133."""
+    if num_updates < warmup_updates:
+        return warmup_init_lr + num_updates * (lr - warmup_init_lr) / warmup_updates
+    return lr * warmup_updates ** exp_factor * (num_updates ** -exp_factor)
+
+
 def synthetic_batch(B, T, R, n_words, sample_n=4, seed=1234, ragged=False, n_mask_text=None, n_mask_img=None,
                     feat_dim=2048):
     g = torch.Generator().manual_seed(seed)

@@ -109,9 +109,43 @@ def run_case(name, emb_dim, n_layers, n_heads, n_words, B, T, R, n_langs, ragged
     return out, keys
 
 
+def run_optimizer_case(seed=3, n=1003, steps=6, max_norm=5.0):
+    """Trainer.optimize's clip + step (xtrainer.py:222-228) with the reference's own AdamInverseSqrtWithWarmup
+    (optim.py:89-139) on two parameter tensors and seeded gradients; `get_optimizer` itself cannot run on
+    Python >= 3.11 (inspect.getargspec, optim.py:264), so the class is constructed directly."""
+    import warnings
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from src.optim import AdamInverseSqrtWithWarmup
+    g = torch.Generator().manual_seed(seed)
+    params = [torch.nn.Parameter(torch.randn(n, generator=g)), torch.nn.Parameter(torch.randn(17, 5, generator=g))]
+    kw = dict(lr=1e-2, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01, warmup_updates=3, warmup_init_lr=1e-4)
+    opt = AdamInverseSqrtWithWarmup(params, **kw)
+    out = {"kw": kw, "max_norm": max_norm, "p0": [p.detach().clone() for p in params], "grads": [], "params": [],
+           "lrs": [], "norms": []}
+    for s in range(steps):
+        scale = 40.0 if s % 2 == 0 else 0.05  # alternate clipped / unclipped steps
+        grads = [torch.randn(p.shape, generator=g) * scale for p in params]
+        for p, gr in zip(params, grads):
+            p.grad = gr.clone()
+        norm = torch.nn.utils.clip_grad_norm_(params, max_norm)
+        out["lrs"].append(opt.param_groups[0]["lr"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            opt.step()
+        out["grads"].append(grads)
+        out["norms"].append(float(norm))
+        out["params"].append([p.detach().clone() for p in params])
+    return out
+
+
 if __name__ == "__main__":
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
+    torch.save(run_optimizer_case(), os.path.join(gold, "adam_inverse_sqrt.pt"))
+    print("adam_inverse_sqrt.pt", os.path.getsize(os.path.join(gold, "adam_inverse_sqrt.pt")))
+    if "--optimizer-only" in sys.argv:
+        sys.exit(0)
     # C1 of BASELINE.json: 2 layers / 128 hidden, 16 text + 4 region tokens, batch 2
     c1, keys = run_case("c1", 128, 2, 2, 1000, B=2, T=16, R=4, n_langs=1, ragged=False, seed=0)
     torch.save(c1, os.path.join(gold, "c1_tiny.pt"))

@@ -481,3 +481,64 @@ def test_cuda_graph_step_matches_eager_and_redraws_dropout(m3p):
         losses.append(float(gd.step()))
         torch.cuda.synchronize()
     assert len(set(losses)) == 3 and all(l == l for l in losses)
+
+
+# ---------------------------------------------------------------------------------------------------
+# optimizer: fused clip + Adam over the flat buffers
+# ---------------------------------------------------------------------------------------------------
+def test_fused_adam_matches_reference_golden(m3p, golden_dir):
+    """m3p_sumsq_f32 + m3p_adam_step through m3p_b200.optim reproduce the reference's clip_grad_norm_ +
+    AdamInverseSqrtWithWarmup trajectory (tests/golden/adam_inverse_sqrt.pt, generated from the reference)."""
+    from m3p_b200 import optim
+    g = torch.load(os.path.join(golden_dir, "adam_inverse_sqrt.pt"), weights_only=False)
+    kw = dict(g["kw"])
+    params = [torch.nn.Parameter(p.clone().cuda()) for p in g["p0"]]
+    opt = optim.AdamInverseSqrtWithWarmup(params, clip_grad_norm=g["max_norm"], **kw)
+    for grads, want, want_lr, want_norm in zip(g["grads"], g["params"], g["lrs"], g["norms"]):
+        assert abs(opt.param_groups[0]["lr"] - want_lr) <= 1e-9 * abs(want_lr) + 1e-12
+        for p, gr in zip(params, grads):
+            p.grad = gr.clone().cuda()
+        opt.step()
+        assert abs(float(opt.last_grad_norm.sqrt()) - want_norm) < 1e-4 * want_norm
+        for p, w in zip(params, want):
+            assert _rel(p.detach(), w.cuda()) < 2e-6
+            assert float(p.grad.abs().max()) == 0.0  # zeroed in the same pass
+
+
+def test_fused_adam_on_the_model_flat_buffers(m3p):
+    """One optimizer step on a TransformerModel: every trained parameter follows the oracle's Adam, the bf16
+    operand copy is refreshed by the step (no cast kernel in the next forward), the gradients are cleared, and
+    training reduces the loss."""
+    from m3p_b200 import ops, optim
+    from m3p_b200.train_step import pretrain_step, synthetic_batch
+    from oracle import m3p_oracle as O
+    ns = _ns(128, 2, 2, 500)
+    model = _model(m3p, ns)
+    b = synthetic_batch(4, 12, 5, ns.n_words, sample_n=2, seed=2, n_mask_text=2, n_mask_img=1, device="cuda")
+    opt = optim.get_optimizer([p for p in model.parameters() if p.requires_grad],
+                              "adam,lr=0.001,beta1=0.9,beta2=0.98", clip_grad_norm=0.05)
+    losses = []
+    for it in range(4):
+        model.zero_grad()
+        total, _ = pretrain_step(model, b, 2)
+        total.backward()
+        losses.append(float(total.detach()))
+        if it == 0:
+            p0, g0 = model._flat.clone(), model._flat_grad.clone()
+            e0, ge0 = model._emb.data.clone(), model._emb_grad.clone()
+        opt.step()
+        if it == 0:
+            coef, _ = O.clip_coef([g0.cpu(), ge0.cpu()], 0.05)
+            assert float(coef) < 1.0  # the clip is active
+            for p_new, p_old, gr in ((model._flat, p0, g0), (model._emb.data, e0, ge0)):
+                want = O.adam_step(p_old.cpu().clone(), gr.cpu() * coef, torch.zeros_like(gr.cpu()),
+                                   torch.zeros_like(gr.cpu()), 1, 0.001, (0.9, 0.98), 1e-8)
+                assert _rel(p_new, want.cuda()) < 1e-6
+            assert torch.equal(model._flat16, model._flat.bfloat16())
+            assert float(model._flat_grad.abs().max()) == 0.0 and float(model._emb_grad.abs().max()) == 0.0
+            assert model._operands_valid and model._grads_clean
+            n0 = ops.LAUNCHES
+            model.zero_grad()           # nothing to clear
+            model.refresh_operands()    # nothing to cast
+            assert ops.LAUNCHES == n0
+    assert losses[-1] < losses[0]

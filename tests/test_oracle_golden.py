@@ -95,3 +95,22 @@ def test_get_masks_matches_reference_semantics():
     mask, attn = O.get_masks(5, lengths)
     assert mask.tolist() == [[True] * 3 + [False] * 2, [False] * 5, [True] * 5]
     assert attn is mask
+
+
+def test_optimizer_oracle_matches_reference_adam(golden_dir):
+    """clip_grad_norm_ + AdamInverseSqrtWithWarmup (xtrainer.py:222-228, optim.py:45-139): the oracle's
+    restatement reproduces the reference's parameters after every one of 6 steps (clipped and unclipped)."""
+    g = torch.load(os.path.join(golden_dir, "adam_inverse_sqrt.pt"), weights_only=False)
+    kw = g["kw"]
+    params = [p.clone() for p in g["p0"]]
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+    lr = kw["warmup_init_lr"]
+    for s, (grads, want, want_lr, want_norm) in enumerate(zip(g["grads"], g["params"], g["lrs"], g["norms"])):
+        assert abs(lr - want_lr) <= 1e-12 + 1e-9 * abs(want_lr)
+        coef, total = O.clip_coef(grads, g["max_norm"])
+        assert abs(float(total) - want_norm) < 1e-4 * want_norm
+        for p, gr, mi, vi, w in zip(params, grads, m, v, want):
+            O.adam_step(p, gr * coef, mi, vi, s + 1, lr, kw["betas"], kw["eps"], kw["weight_decay"])
+            assert _close(p, w, 1e-6)
+        lr = O.lr_inverse_sqrt(s + 1, kw["lr"], kw["warmup_updates"], kw["warmup_init_lr"])
