@@ -291,6 +291,11 @@ typedef struct m3p_embed_bwd_args {
   float* d_pos_emb;
   float* d_lang_emb;
   float* dy_img;
+  /* M3P_EMB_DROP2 without M3P_EMB_LN (crossfwd image stream, transformer.py:1044-1049: a second dropout straight
+   * after BertImageEmbeddings, no layer_norm_emb): its mask is re-applied to dy_pre here.  With M3P_EMB_LN the
+   * dropout sits behind the LayerNorm and m3p_layernorm_bwd(dy_drop_p) handles it. */
+  float drop_p;
+  uint64_t seed_emb;
 } m3p_embed_bwd_args;
 M3P_API int m3p_embed_bwd_route(const m3p_embed_bwd_args* args, m3p_stream_t stream);
 /* d w_loc[j][c] += sum_rows de[row][j] * image_loc[row][c] (autograd of :261, K = 5). */

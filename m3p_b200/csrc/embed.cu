@@ -211,8 +211,10 @@ embed_fwd_kernel(const m3p_embed_args a, const uint32_t thr16, const float scale
 //               d_lang_emb[lang] += g
 //   image row : dy_img[b*R + s] = g      (input of the LayerNorm_img backward)
 __global__ void __launch_bounds__(EMB_THREADS)
-embed_bwd_route_kernel(const m3p_embed_bwd_args a) {
+embed_bwd_route_kernel(const m3p_embed_bwd_args a, const uint32_t thr16, const float scale, const uint64_t* seed_mix) {
   const int lane = threadIdx.x & 31;
+  uint32_t se_lo = (uint32_t)(a.seed_emb & 0xffffffffu), se_hi = (uint32_t)(a.seed_emb >> 32);
+  if (thr16 != 0) mix_seed(seed_mix, se_lo, se_hi);
   const int d = (int)a.d;
   const long long S = a.R + a.T;
   const long long rows = a.B * S;
@@ -238,12 +240,21 @@ embed_bwd_route_kernel(const m3p_embed_bwd_args a) {
       if (a.positions != nullptr) pidx = a.positions[t * a.B + b];
       if (a.langs != nullptr && a.d_lang_emb != nullptr) dlang = a.d_lang_emb + a.langs[t * a.B + b] * d;
     }
-    // rows removed by the pre-LN mask carry no gradient to the embeddings (transformer.py:940)
-    const bool live = !((a.flags & M3P_EMB_MASK_PRE) && !valid);
+    // rows removed by the mask (before the LayerNorm, transformer.py:940, or after the dropout, :831 / :1062)
+    // carry no gradient to the embeddings
+    const bool live = !((a.flags & (M3P_EMB_MASK_PRE | M3P_EMB_MASK_POST)) && !valid);
     float* dpos = ((a.flags & M3P_EMB_POS) && a.d_pos_emb != nullptr) ? a.d_pos_emb + pidx * d : nullptr;
     for (int c = lane; c < (d >> 2); c += 32) {
       float4 v = *reinterpret_cast<const float4*>(g + c * 4);
       if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (thr16 != 0) {  // the forward's second dropout (same element counter as embed_fwd_kernel)
+        const uint32_t e0 = (uint32_t)row * (uint32_t)d + (uint32_t)c * 4u;
+        const uint32_t h0 = drop_hash(e0 >> 1, se_lo, se_hi), h1 = drop_hash((e0 >> 1) + 1, se_lo, se_hi);
+        v.x = ((h0 & 0xffffu) >= thr16) ? v.x * scale : 0.f;
+        v.y = ((h0 >> 16) >= thr16) ? v.y * scale : 0.f;
+        v.z = ((h1 & 0xffffu) >= thr16) ? v.z * scale : 0.f;
+        v.w = ((h1 >> 16) >= thr16) ? v.w * scale : 0.f;
+      }
       if (dcopy) *reinterpret_cast<float4*>(dcopy + c * 4) = v;
       if (live) {
         if (dpos) atomicAdd(reinterpret_cast<float4*>(dpos + c * 4), v);
@@ -317,7 +328,10 @@ extern "C" int m3p_embed_bwd_route(const m3p_embed_bwd_args* a, m3p_stream_t str
   const long long rows = a->B * (a->R + a->T);
   long long g = (rows + EMB_WARPS - 1) / EMB_WARPS;
   const long long cap = (long long)sm_count() * 8;
-  embed_bwd_route_kernel<<<(int)(g < cap ? g : cap), EMB_THREADS, 0, stream>>>(*a);
+  M3P_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, "m3p_embed_bwd_route: drop_p out of range");
+  const bool drop = (a->flags & M3P_EMB_DROP2) && !(a->flags & M3P_EMB_LN) && a->drop_p > 0.f;
+  embed_bwd_route_kernel<<<(int)(g < cap ? g : cap), EMB_THREADS, 0, stream>>>(*a, drop ? drop_thr16(a->drop_p) : 0u,
+                                                                          1.0f / (1.0f - a->drop_p), seed_mix_ptr());
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }

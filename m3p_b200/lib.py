@@ -77,6 +77,7 @@ class EmbedBwdArgs(ctypes.Structure):
         ("pad_index", c_int64),
         ("d_tok_emb", c_void_p), ("d_text_embed", c_void_p), ("d_pos_emb", c_void_p), ("d_lang_emb", c_void_p),
         ("dy_img", c_void_p),
+        ("drop_p", c_float), ("seed_emb", c_uint64),
     ]
 
 

@@ -482,9 +482,16 @@ class TransformerModel(nn.Module):
         if causal or src_enc is not None or cache is not None or refine_image or refine_encoder or image_fusion \
                 or image_dist is not None or is_latent:
             raise NotImplementedError("crossfwd: causal / decoder / cache / refine / fusion are outside the B200 path")
-        if stream_ == 'img':
-            raise NotImplementedError("crossfwd(stream_='img') (second dropout on the image stream) is not built yet")
         self._require_cuda(x)
+        if stream_ == 'img':
+            # image stream (:1044-1049): BertImageEmbeddings -> dropout -> mask, no layer_norm_emb
+            if langs is not None:
+                raise NotImplementedError("crossfwd(stream_='img') with langs: the reference runs it with langs=None "
+                                          "('currently we set langs=None', transformer.py:1046); not built")
+            assert image_loc is not None and lengths.size(0) == x.size(1)
+            spec = dict(kind="image", B=x.size(1), T=0, R=x.size(0), x=None, lengths=lengths, x_img=x, image_loc=image_loc,
+                        positions=None, langs=None, flags=L.M3P_EMB_DROP2 | L.M3P_EMB_MASK_POST)
+            return _EncoderFn.run(self, spec, x, None)
         slen, bs = x.size()
         assert lengths.size(0) == bs
         if positions is not None:
@@ -732,6 +739,7 @@ class TransformerModel(nn.Module):
         b.B, b.R, b.T, b.d, b.flags = B, R, T, d, flags
         b.dy_pre, b.seqlen = dy_pre.data_ptr(), seqlen.data_ptr()
         b.pad_index = self.pad_index
+        b.drop_p, b.seed_emb = p_drop, st["seed"] ^ 0x2222
         if T > 0:
             b.x = st["x"].data_ptr()
             if want_dtext:

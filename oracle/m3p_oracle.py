@@ -35,8 +35,42 @@ def get_masks(slen, lengths, causal=False):
     return mask, mask
 
 
+# ---- rounding-matched mode ---------------------------------------------------------------------------
+# `with rounding_matched():` makes the SAME restatement round to bf16 at exactly the points where the B200 kernels
+# do (tensor-core operands = weights and stored activations; fp32 accumulation, softmax, LayerNorm statistics,
+# biases, residual adds and losses stay fp32), with a straight-through gradient.  What remains between this
+# mode and the kernels is accumulation order (and a rare 1-ulp flip of a bf16 rounding), which is what the
+# north_star's 1e-3 bound can meaningfully be stated against; the default mode is the reference's fp32 math.
+_ROUND = False
+
+
+class _RoundSTE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _r(x):
+    return _RoundSTE.apply(x) if _ROUND else x
+
+
+class rounding_matched:
+    def __enter__(self):
+        global _ROUND
+        self.prev, _ROUND = _ROUND, True
+
+    def __exit__(self, *exc):
+        global _ROUND
+        _ROUND = self.prev
+
+
 def _linear(sd, prefix, x):
-    return F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
+    """nn.Linear; in rounding-matched mode the two GEMM operands are bf16, the bias and the result fp32."""
+    return F.linear(_r(x), _r(sd[prefix + ".weight"]), sd[prefix + ".bias"])
 
 
 def _layer_norm(sd, prefix, x):
@@ -46,7 +80,8 @@ def _layer_norm(sd, prefix, x):
 def image_embeddings(sd, x_img, image_loc):
     """BertImageEmbeddings.forward — transformer.py:247-269 (input_dist is None on this path)."""
     e = _linear(sd, "image_embeddings.image_embeddings", x_img) + \
-        _linear(sd, "image_embeddings.image_location_embeddings", image_loc)
+        F.linear(image_loc, sd["image_embeddings.image_location_embeddings.weight"],
+                 sd["image_embeddings.image_location_embeddings.bias"])  # K = 5: plain fp32 FMAs in the kernel
     return _layer_norm(sd, "image_embeddings.LayerNorm", e)
 
 
@@ -59,30 +94,36 @@ def attention(sd, i, n_heads, h, mask):
     def shape(x):
         return x.view(bs, -1, n_heads, dh).transpose(1, 2)
 
-    q = shape(_linear(sd, p + "q_lin", h))
-    k = shape(_linear(sd, p + "k_lin", h))
-    v = shape(_linear(sd, p + "v_lin", h))
-    q = q / math.sqrt(dh)                                   # :197 (after the bias)
+    q = shape(_r(_linear(sd, p + "q_lin", h)))              # the packed QKV projection is stored in bf16
+    k = shape(_r(_linear(sd, p + "k_lin", h)))
+    v = shape(_r(_linear(sd, p + "v_lin", h)))
+    q = q / math.sqrt(dh)                                   # :197 (after the bias; 1/8 is exact in bf16)
     scores = torch.matmul(q, k.transpose(2, 3))             # :198
     scores = scores.masked_fill((mask == 0).view(bs, 1, 1, qlen), -float("inf"))  # :199-200
-    weights = F.softmax(scores.float(), dim=-1).type_as(scores)                   # :202
-    ctx = torch.matmul(weights, v).transpose(1, 2).contiguous().view(bs, qlen, dim)  # :204-205
+    if _ROUND:
+        # kernel: p = exp(s - max) enters the P V product as bf16; the row sum is taken over the fp32 values
+        e = torch.exp(scores - scores.max(dim=-1, keepdim=True).values)
+        ctx = torch.matmul(_r(e), v) / e.sum(dim=-1, keepdim=True)
+        ctx = _r(ctx).transpose(1, 2).contiguous().view(bs, qlen, dim)
+    else:
+        weights = F.softmax(scores.float(), dim=-1).type_as(scores)                   # :202
+        ctx = torch.matmul(weights, v).transpose(1, 2).contiguous().view(bs, qlen, dim)  # :204-205
     return _linear(sd, p + "out_lin", ctx)                  # :208
 
 
 def ffn(sd, i, h):
     """TransformerFFN.forward — transformer.py:222-227."""
     p = "ffns.%d." % i
-    return _linear(sd, p + "lin2", gelu(_linear(sd, p + "lin1", h)))
+    return _linear(sd, p + "lin2", _r(gelu(_linear(sd, p + "lin1", h))))
 
 
 def layers(sd, n_layers, n_heads, h, mask):
     """The layer loop shared by fwd / jointfwd / crossfwd — transformer.py:947-958, 842-864."""
     m = mask.unsqueeze(-1).to(h.dtype)
     for i in range(n_layers):
-        h = _layer_norm(sd, "layer_norm1.%d" % i, h + attention(sd, i, n_heads, h, mask))
-        h = _layer_norm(sd, "layer_norm2.%d" % i, h + ffn(sd, i, h))
-        h = h * m
+        # the kernels store the pre-LayerNorm sums and the LayerNorm outputs in bf16
+        h = _r(_layer_norm(sd, "layer_norm1.%d" % i, _r(h + attention(sd, i, n_heads, h, mask))))
+        h = _r(_layer_norm(sd, "layer_norm2.%d" % i, _r(h + ffn(sd, i, h))) * m)
     return h
 
 
@@ -100,7 +141,7 @@ def jointfwd(sd, n_layers, n_heads, x, lengths, x_img, lengths_img, image_loc, t
     h = torch.cat([img, txt], dim=1)                                                    # :929
     h = h + sd["position_embeddings.weight"][:c_slen].unsqueeze(0)                      # :932-936
     h = h * mask.unsqueeze(-1).to(h.dtype)                                              # :940
-    h = _layer_norm(sd, "layer_norm_emb", h)                                            # :942
+    h = _r(_layer_norm(sd, "layer_norm_emb", h))                                        # :942
     h = layers(sd, n_layers, n_heads, h, mask)
     return h.transpose(0, 1)
 
@@ -118,7 +159,7 @@ def crossfwd_text(sd, n_layers, n_heads, x, lengths, positions=None, langs=None,
     if langs is not None:
         h = h + F.embedding(langs.transpose(0, 1), sd["cross_lang_embeddings.weight"])   # :1056-1057
     h = _layer_norm(sd, "layer_norm_emb", h)                                            # :1058
-    h = h * mask.unsqueeze(-1).to(h.dtype)                                              # :1062
+    h = _r(h * mask.unsqueeze(-1).to(h.dtype))                                          # :1062
     h = layers(sd, n_layers, n_heads, h, mask)
     return h.transpose(0, 1)
 
@@ -134,7 +175,7 @@ def fwd_image(sd, n_layers, n_heads, x_img, lengths, image_loc):
     R, bs = x_img.shape[0], x_img.shape[1]
     mask, _ = get_masks(R, lengths)
     h = image_embeddings(sd, x_img.transpose(0, 1), image_loc.transpose(0, 1))
-    h = h * mask.unsqueeze(-1).to(h.dtype)
+    h = _r(h * mask.unsqueeze(-1).to(h.dtype))
     h = layers(sd, n_layers, n_heads, h, mask)
     return h.transpose(0, 1)
 
@@ -145,28 +186,28 @@ def predict_mlm(sd, tensor, pred_mask, y):
     """default branch -> PredLayer.forward (:104-117); tensor (S',B,d), pred_mask (S',B) bool."""
     dim = tensor.shape[-1]
     rows = tensor[pred_mask.unsqueeze(-1).expand_as(tensor)].view(-1, dim)
-    scores = F.linear(rows, sd["pred_layer.proj.weight"], sd["pred_layer.proj.bias"])
+    scores = _r(F.linear(_r(rows), _r(sd["pred_layer.proj.weight"]), sd["pred_layer.proj.bias"]))  # bf16 logits
     return scores, F.cross_entropy(scores, y, reduction="mean")
 
 
 def predict_obj(sd, tensor, y):
     """is_obj: BertPredictionHeadTransform (:602-606) -> ObjPredLayer (:576-584); tensor (B,R,d)."""
-    t = _layer_norm(sd, "transformer_obj.LayerNorm", gelu(_linear(sd, "transformer_obj.dense", tensor)))
-    scores = _linear(sd, "pred_obj_layer.proj", t).view(-1, sd["pred_obj_layer.proj.weight"].shape[0])
+    t = _r(_layer_norm(sd, "transformer_obj.LayerNorm", _r(gelu(_linear(sd, "transformer_obj.dense", tensor)))))
+    scores = _r(_linear(sd, "pred_obj_layer.proj", t)).view(-1, sd["pred_obj_layer.proj.weight"].shape[0])
     return scores, F.cross_entropy(scores, y, reduction="mean", ignore_index=-1)
 
 
 def predict_mrfr(sd, tensor):
     """is_mrfr (:1202-1204)."""
-    return _linear(sd, "mrfr_dense", tensor)
+    return _r(_linear(sd, "mrfr_dense", tensor))
 
 
 def predict_relation(sd, tensor, clcm=False):
     """is_relation / is_clcm: BertPooler (:552-558) on position 0 of the batch-first tensor, then
     seq_relationship (:713,1195-1201)."""
     pl, sr = ("pooled_layer2", "seq_relationship2") if clcm else ("pooled_layer", "seq_relationship")
-    pooled = torch.tanh(_linear(sd, pl + ".dense", tensor[:, 0]))
-    return _linear(sd, sr, pooled)
+    pooled = _r(torch.tanh(_linear(sd, pl + ".dense", tensor[:, 0])))
+    return F.linear(pooled, sd[sr + ".weight"], sd[sr + ".bias"])  # 1-row projection: fp32 weights in the kernel
 
 
 # ---- loss assembly: XTrainer.pretrain_under_step — xtrainer.py:2285-2375 ---------------------------

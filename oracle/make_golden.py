@@ -99,6 +99,8 @@ def run_case(name, emb_dim, n_layers, n_heads, n_words, B, T, R, n_langs, ragged
                                            stream_="text", langs=langs)
         out["fwd_image"] = m("fwd", x=batch["x_img"], lengths=batch["lengths_img"], causal=False, cross_modal=True,
                              image_loc=batch["image_loc"])
+        out["crossfwd_img"] = m("crossfwd", x=batch["x_img"], lengths=batch["lengths_img"], causal=False, stream_="img",
+                                langs=None, cross_modal=True, image_loc=batch["image_loc"])
     sd = m.state_dict()
     out["state_dict"] = {k: v.clone() for k, v in sd.items()
                          if not k.startswith(("refine_embeddings", "cross_alignment", "encoder_attn", "layer_norm15",
