@@ -99,6 +99,11 @@ typedef struct m3p_gemm_args {
   int64_t ldaux;
   float drop_p; /* M3P_EPI_DROP_RES: 0 disables */
   uint64_t seed;
+  /* optional [n] fp32: colsum[j] += sum_rows out[row][j] (the bf16-rounded values that are stored), accumulated
+   * atomically from the epilogue's staging tiles — the bias gradient of the layer whose output gradient this GEMM
+   * produces (e.g. d b1 of the FFN from the lin2 dgrad, transformer.py:223), saving a pass over `out`.
+   * bf16 outputs on the TMA path only (16-byte aligned bases and pitches); otherwise M3P_ERR_UNSUPPORTED. */
+  float* colsum;
 } m3p_gemm_args;
 
 M3P_API int m3p_gemm_bf16(const m3p_gemm_args* args, m3p_stream_t stream);

@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                 const __grid_constant__ CUtensorMap tmap_ctx, const AttnKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment as an OFFSET from the __shared__ array, so every derived pointer keeps its shared-memory
+  // provenance and the compiler emits LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 16 * 1024;
   uint8_t* sV = smem + 64 * 1024;
@@ -351,8 +352,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_dqkv,
                 const AttnKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment as an OFFSET from the __shared__ array, so every derived pointer keeps its shared-memory
+  // provenance and the compiler emits LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 32 * 1024;
   uint8_t* sV = smem + 64 * 1024;

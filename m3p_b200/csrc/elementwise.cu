@@ -38,6 +38,28 @@ __device__ __forceinline__ void drop8(uint32_t e0, uint32_t seed_lo, uint32_t se
   }
 }
 
+// 8 elements kept as loaded (16 bytes of bf16 / 32 bytes of fp32) so that several rows can be in flight per thread
+// without holding their unpacked floats in registers
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float* f) const {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void unpack(float* f) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+
 constexpr int EW_THREADS = 256;
 constexpr int EW_WARPS = EW_THREADS / 32;
 
@@ -246,8 +268,9 @@ static ColGeom col_geom(long long rows, int n) {
 
 // Pass 2 — column sums over rows: dgamma = sum dy_eff * xhat, dbeta = sum dy_eff, dbias = sum dx_drop.
 // dy / x were just read by pass 1 and dx_drop just written, so this pass mostly hits L2.
+constexpr int LNC_U = 4;  // rows in flight per thread (3 x 16-byte loads each): the pass is latency-bound
 template <typename XT, typename DYT, typename BT>
-__global__ void __launch_bounds__(EW_THREADS)
+__global__ void __launch_bounds__(EW_THREADS, 2)
 ln_bwd_cols_kernel(const LnBwdParams p, const BT* __restrict__ bias_src, int tx, long long rows_per_block) {
   extern __shared__ float sred[];  // [ty][tx * 8]
   const int d = p.d;
@@ -266,42 +289,50 @@ ln_bwd_cols_kernel(const LnBwdParams p, const BT* __restrict__ bias_src, int tx,
   uint32_t dy_lo = p.dy_seed_lo, dy_hi = p.dy_seed_hi;
   if (p.dy_thr16 != 0) mix_seed(p.seed_mix, dy_lo, dy_hi);
   if (col_ok) {
-    for (long long r = r0 + ry; r < r1; r += 2 * ty) {
-      float xv[2][8], dv[2][8], bv[2][8], mean[2], rstd[2];
-      bool ok[2];
+    for (long long r = r0 + ry; r < r1; r += LNC_U * ty) {
+      Raw8<XT> xr[LNC_U];
+      Raw8<DYT> dr[LNC_U];
+      Raw8<BT> br[LNC_U];
+      float mean[LNC_U], rstd[LNC_U];
+      bool ok[LNC_U];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < LNC_U; ++i) {
         const long long row = r + (long long)i * ty;
         ok[i] = row < r1;
         const long long rr = ok[i] ? row : r0;
         if (want_gb) {
-          load8(x + rr * d + col0, xv[i]);
-          load8(dy + rr * d + col0, dv[i]);
+          xr[i].load(x + rr * d + col0);
+          dr[i].load(dy + rr * d + col0);
           mean[i] = p.mean[rr];
           rstd[i] = p.rstd[rr];
         }
-        if (bias_src != nullptr) load8(bias_src + rr * d + col0, bv[i]);
+        if (bias_src != nullptr) br[i].load(bias_src + rr * d + col0);
       }
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < LNC_U; ++i) {
         const long long row = r + (long long)i * ty;
         if (!ok[i]) continue;
         if (want_gb) {
           bool valid = true;
           if (p.seqlen != nullptr) valid = (row % p.S) < p.seqlen[row / p.S];
           if (valid) {
+            float xv[8], dv[8];
+            xr[i].unpack(xv);
+            dr[i].unpack(dv);
             if (p.dy_thr16 != 0)
-              drop8((uint32_t)row * (uint32_t)d + col0, dy_lo, dy_hi, p.dy_thr16, p.dy_scale, dv[i]);
+              drop8((uint32_t)row * (uint32_t)d + col0, dy_lo, dy_hi, p.dy_thr16, p.dy_scale, dv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              ag[j] = fmaf(dv[i][j], (xv[i][j] - mean[i]) * rstd[i], ag[j]);
-              ab[j] += dv[i][j];
+              ag[j] = fmaf(dv[j], (xv[j] - mean[i]) * rstd[i], ag[j]);
+              ab[j] += dv[j];
             }
           }
         }
         if (bias_src != nullptr) {
+          float bv[8];
+          br[i].unpack(bv);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) abias[j] += bv[i][j];
+          for (int j = 0; j < 8; ++j) abias[j] += bv[j];
         }
       }
     }

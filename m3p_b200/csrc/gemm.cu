@@ -66,6 +66,7 @@ struct GemmKernelParams {
   int accumulate;
   int vec_ok;  // all pitches / bases allow 16-byte vector access
   int tma_store;  // bf16 outputs leave through smem staging + cp.async.bulk.tensor stores
+  float* colsum;  // optional [N]: += column sums of the stored (bf16-rounded) output
 };
 
 __device__ __forceinline__ void decode_unit(const GemmKernelParams& p, int u, int& m_tile,
@@ -270,8 +271,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr int NCTA = CTA2 ? 2 : 1;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment as an OFFSET from the __shared__ array, so every derived pointer keeps its shared-memory
+  // provenance and the compiler emits LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stg_smem = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned: STAGE_BYTES is a multiple of 1024
   float* bias_smem = reinterpret_cast<float*>(stg_smem + Cfg::STG_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES + Cfg::BIAS_BYTES);
@@ -433,27 +435,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if constexpr (EPI == M3P_EPI_DROP_RES) mix_seed(p.seed_mix, seed_lo, seed_hi);
 
     // Staging groups are numbered gg = 0, 1, ... over ALL tiles of this warp (NG per tile); the static tile
-    // schedule makes the coordinates of any future group a pure function of gg, so the aux tile of group gg + 2
-    // (possibly the next tile's) can be requested while group gg + 1 is being computed.
-    auto group_coords = [&](int gg, int& col0, int& row0) -> bool {
-      const long long u = unit0 + static_cast<long long>(gg / NG) * unit_stride;
-      if (u >= p.num_units) return false;
-      int m_tile, n_tile, ks;
-      decode_unit(p, static_cast<int>(u), m_tile, n_tile, ks);
-      col0 = n_tile * BN + cbase + (gg % NG) * GW;
-      row0 = (m_tile * NCTA + (int)cta_rank) * BLOCK_M + q * 32;
-      return col0 < p.N && row0 < p.M;  // a box entirely outside the tensor is neither loaded nor stored
-    };
-    auto issue_aux = [&](int gg) {  // lane 0
-      int col0, row0;
-      if (group_coords(gg, col0, row0)) {
-        const int b = gg % RING;
-        mbar_arrive_expect_tx(&my_aux_bar[b], STG_TILE);
-        tma_load_2d(ring + b * STG_TILE, &tmap_aux, &my_aux_bar[b], col0, row0);
+    // schedule makes the coordinates of any future group known in advance, so the aux tile of group gg + 2
+    // (possibly the next tile's) is requested while group gg + 1 is being computed.  The request cursor below
+    // walks the same sequence two groups ahead (one unit decode per tile, no per-group divisions).
+    long long ax_u = unit0;      // unit of the group the cursor points at
+    int ax_g = 0, ax_slot = 0;   // its group index inside the tile and its ring slot
+    int ax_col = 0, ax_row0 = 0; // first column of the tile's slice for this warp / first row of its sub-tile
+    auto ax_decode = [&]() {
+      if (ax_u < p.num_units) {
+        int m_tile, n_tile, ks;
+        decode_unit(p, static_cast<int>(ax_u), m_tile, n_tile, ks);
+        ax_col = n_tile * BN + cbase;
+        ax_row0 = (m_tile * NCTA + (int)cta_rank) * BLOCK_M + q * 32;
       }
     };
+    auto issue_aux = [&]() {  // lane 0: request the cursor's group, then advance the cursor
+      const int col0 = ax_col + ax_g * GW;
+      if (ax_u < p.num_units && col0 < p.N && ax_row0 < p.M) {  // a box entirely outside the tensor is skipped
+        mbar_arrive_expect_tx(&my_aux_bar[ax_slot], STG_TILE);
+        tma_load_2d(ring + ax_slot * STG_TILE, &tmap_aux, &my_aux_bar[ax_slot], col0, ax_row0);
+      }
+      if (++ax_slot == RING) ax_slot = 0;
+      if (++ax_g == NG) { ax_g = 0; ax_u += unit_stride; ax_decode(); }
+    };
     if constexpr (HAS_AUX) {
-      if (use_tma && lane == 0) { issue_aux(0); issue_aux(1); }
+      if (use_tma && lane == 0) { ax_decode(); issue_aux(); issue_aux(); }
     }
     uint32_t aux_phase = 0;  // bit b: parity the next wait on ring slot b expects
     int gg = 0;
@@ -527,6 +533,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           fence_proxy_async_smem();
           __syncwarp();
+          if (p.colsum != nullptr && valid) {
+            // column sums of the staged [32 rows][32 cols] tile: lane = (row parity, column pair); the two half-warps
+            // read rows of opposite parity (64-byte rows: two consecutive rows cover all 32 banks)
+            const int cp = lane & 15, par = lane >> 4;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int r2 = 0; r2 < 16; ++r2) {
+              const int r = 2 * r2 + par;
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(slot + stg_off(r, cp >> 2) + (cp & 3) * 4);
+              if (row0 + r < p.M) { s0 += bf16_lo(w); s1 += bf16_hi(w); }
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            const int col = gcol0 + 2 * cp;
+            if (par == 0 && col < p.N) atomicAdd(p.colsum + col, s0);
+            if (par == 1 && col + 1 < p.N) atomicAdd(p.colsum + col + 1, s1);
+          }
 #ifdef M3P_GEMM_TRACE
           if (gg >= NG && gg < 2 * NG) GT_MARK();  // epi (2nd tile): group computed and staged
 #endif
@@ -538,7 +561,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tma_store_commit();  // one bulk group per staging group, valid or not: keeps the wait counts uniform
             if constexpr (HAS_AUX) {
               tma_store_wait_read<1>();  // every store but the one just issued has been read: slot (gg + 2) % 3 is free
-              issue_aux(gg + 2);
+              issue_aux();
             }
           }
 #ifdef M3P_GEMM_TRACE
@@ -724,6 +747,7 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   p.seed_hi = (uint32_t)(a->seed >> 32);
   p.seed_mix = seed_mix_ptr();
   p.accumulate = a->accumulate;
+  p.colsum = a->colsum;
   {
     const int osz = a->out_f32 ? 4 : 2;
     bool ok = aligned16(a->out) && ((a->ldo * osz) % 16 == 0);
@@ -757,6 +781,10 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
       rc = get_tmap_2d_bf16(&tx, a->aux, (uint64_t)a->n, (uint64_t)a->m, (uint64_t)a->ldaux, GW, 32);
       if (rc) return rc;
     }
+  }
+  if (a->colsum != nullptr && !p.tma_store) {
+    set_last_error("m3p_gemm_bf16: colsum needs a bf16 output on the TMA path (16-byte aligned bases and pitches)");
+    return M3P_ERR_UNSUPPORTED;
   }
   if (cta2) {
     if (BN == 256) return dispatch_epi<256, true>(ta, tb, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);

@@ -30,6 +30,7 @@ class GemmArgs(ctypes.Structure):
         ("out2", c_void_p), ("ldo2", c_int64),
         ("aux", c_void_p), ("ldaux", c_int64),
         ("drop_p", c_float), ("seed", c_uint64),
+        ("colsum", c_void_p),
     ]
 
 

@@ -77,7 +77,7 @@ def split_k_for(m, n, k):
 
 def gemm(a, b, m, n, k, out, *, lda=None, ldb=None, ldo=None, a_mn=False, b_mn=False, epi=L.M3P_EPI_LINEAR,
          out_f32=False, accumulate=False, split_k=1, alpha=1.0, bias=None, out2=None, ldo2=None, aux=None,
-         ldaux=None, drop_p=0.0, seed=0):
+         ldaux=None, drop_p=0.0, seed=0, colsum=None):
     """C[m][n] = sum_k A(m,k) B(n,k) with a fused epilogue (see m3p_gemm_bf16 in the header)."""
     g = L.GemmArgs()
     g.a, g.b = a.data_ptr(), b.data_ptr()
@@ -98,6 +98,7 @@ def gemm(a, b, m, n, k, out, *, lda=None, ldb=None, ldo=None, a_mn=False, b_mn=F
         g.aux = aux.data_ptr()
         g.ldaux = aux.stride(0) if ldaux is None else ldaux
     g.drop_p, g.seed = drop_p, seed
+    g.colsum = _p(colsum)
     L.check(_lib().m3p_gemm_bf16(_byref(g), _stream()), "m3p_gemm_bf16")
     return out
 

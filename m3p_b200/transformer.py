@@ -691,10 +691,9 @@ class TransformerModel(nn.Module):
             sq.run(lambda: ops.wgrad(dx2d_, s["g"], gr["w2"]))                  # lin2 wgrad            (:225)
             # lin2 dgrad fused with gelu'(u)                                   (:224-225)
             du = e(M, 4 * d)
-            ops.dgrad(dx2d_, w["w2"], du, epi=L.M3P_EPI_DGELU, aux=s["gp"])
+            ops.dgrad(dx2d_, w["w2"], du, epi=L.M3P_EPI_DGELU, aux=s["gp"], colsum=gr["bb1"])  # + lin1 bias grad
             sq.fork()
-            sq.run(lambda: ops.colsum(du, gr["bb1"]))
-            sq.run(lambda: ops.wgrad(du, s["h1"], gr["w1"]))                    # lin1 wgrad / bias     (:223)
+            sq.run(lambda: ops.wgrad(du, s["h1"], gr["w1"]))                    # lin1 wgrad            (:223)
             # lin1 dgrad + residual branch                                     (:223, :956)
             dh1 = e(M, d)
             ops.dgrad(du, w["w1"], dh1, epi=L.M3P_EPI_DROP_RES, aux=dx2)

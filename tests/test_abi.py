@@ -76,3 +76,16 @@ def test_no_gpu_means_loud_failure(lib):
     from m3p_b200 import lib as L, ops
     with pytest.raises(L.M3PError):
         ops.device_check()
+
+
+def test_train_x_parser_mirrors_reference_flags():
+    """m3p_b200.train_x accepts the reference's flag names (train_x.py:29-391) for the subset the path serves."""
+    from m3p_b200 import train_x
+    p = train_x.get_parser().parse_args(
+        ["--emb_dim", "1024", "--n_layers", "24", "--n_heads", "16", "--gelu_activation", "true", "--batch_size", "24",
+         "--sample_n", "4", "--bptt", "128", "--max_region_num", "100", "--amp", "1", "--fp16", "true",
+         "--accumulate_gradients", "4", "--optimizer", "adam_inverse_sqrt,beta1=0.9,beta2=0.98,lr=0.00005",
+         "--clip_grad_norm", "5", "--cross_rel_steps", "coco-img", "--lambda_rel", "1"])
+    ns = train_x.model_namespace(p)
+    assert (ns.emb_dim, ns.n_layers, ns.n_heads, ns.n_words, ns.pad_index, ns.eos_index) == (1024, 24, 16, 250002, 1, 2)
+    assert p.accumulate_gradients == 4 and p.clip_grad_norm == 5

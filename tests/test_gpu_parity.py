@@ -69,6 +69,24 @@ def test_gemm_operand_layouts(m3p, a_mn, b_mn):
     assert _rel(out, A.float() @ B.float().t()) < KERNEL_TOL
 
 
+@pytest.mark.parametrize("m,n,k", [(304, 392, 200), (1000, 768, 128), (2048, 3072, 64)])
+def test_gemm_epilogue_column_sums(m3p, m, n, k):
+    """m3p_gemm_args.colsum: the bias gradient of the producing layer, accumulated from the staged output tiles
+    (== column sums of the bf16 values the GEMM stores, ragged M / N edges included)."""
+    from m3p_b200 import lib as L, ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    A = (torch.randn(m, k, device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn(n, k, device="cuda", generator=g) * 0.5).bfloat16()
+    aux = torch.randn(m, n, device="cuda", generator=g).bfloat16()
+    bias = torch.randn(n, device="cuda", generator=g)
+    for epi, kw in ((L.M3P_EPI_LINEAR, dict(bias=bias)), (L.M3P_EPI_DGELU, dict(aux=aux))):
+        out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+        cs = torch.full((n,), 3.0, device="cuda")
+        ops.gemm(A, B, m, n, k, out, epi=epi, colsum=cs, **kw)
+        want = out.float().sum(0) + 3.0
+        assert float((cs - want).abs().max()) < 1e-3 * float(want.abs().max()), epi
+
+
 def test_gemm_split_k_accumulates_fp32(m3p):
     from m3p_b200 import ops
     rows, n, k = 1000, 256, 128
@@ -694,3 +712,23 @@ def test_fused_adam_on_the_model_flat_buffers(m3p):
             model.refresh_operands()    # nothing to cast
             assert ops.LAUNCHES == n0
     assert losses[-1] < losses[0]
+
+
+def test_train_x_entry_trains_and_checkpoints(m3p, tmp_path, capsys):
+    """The train_x-compatible entry: reference flag names, all four heads, fused optimizer, CUDA-graphed step;
+    the loss goes down and the checkpoint reloads into a fresh model (xtrainer.py:511-529 layout)."""
+    from m3p_b200 import train_x
+    argv = ["--emb_dim", "128", "--n_layers", "2", "--n_heads", "2", "--n_words", "500", "--dropout", "0.1",
+            "--attention_dropout", "0.1", "--batch_size", "2", "--sample_n", "2", "--bptt", "12", "--max_region_num", "5",
+            "--optimizer", "adam,lr=0.002", "--clip_grad_norm", "5", "--cross_mlm_steps", "x", "--cross_mrm_steps", "x",
+            "--cross_mrfr_steps", "x", "--epoch_size", "480", "--max_epoch", "1", "--dump_path", str(tmp_path)]
+    train_x.main(train_x.get_parser().parse_args(argv))
+    out = capsys.readouterr().out
+    losses = [float(l.split("loss")[1].split("-")[0]) for l in out.splitlines() if " - loss " in l]
+    assert len(losses) >= 4 and losses[-1] < losses[0], out
+    ck = torch.load(os.path.join(str(tmp_path), "checkpoint-0.pth"), weights_only=False)
+    ns = _ns(128, 2, 2, 500)
+    fresh = m3p.TransformerModel(ns, is_encoder=True, with_output=True, is_crossModal=True)
+    missing = fresh.load_state_dict(ck["model"], strict=False)
+    assert not [k for k in missing.missing_keys if not k.startswith("refine_embeddings")]
+    assert ck["params"]["emb_dim"] == 128
