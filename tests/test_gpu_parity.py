@@ -87,6 +87,29 @@ def test_gemm_epilogue_column_sums(m3p, m, n, k):
         assert float((cs - want).abs().max()) < 1e-3 * float(want.abs().max()), epi
 
 
+@pytest.mark.parametrize("m,n,k", [(14592, 768, 768), (14592, 768, 3072), (7296, 768, 2304), (14592, 3072, 768)])
+def test_gemm_at_step_shapes(m3p, m, n, k):
+    """The step's own GEMM shapes (M = 64 pairs x 228 tokens and its half): result, fused residual epilogue and the
+    fused column sums match torch on identical bf16 inputs to the bf16 rounding of the output (1e-3), twice in a
+    row (persistent tile loop, ring-buffered TMA epilogue state)."""
+    from m3p_b200 import lib as L, ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    A = (torch.randn(m, k, device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn(n, k, device="cuda", generator=g) * 0.05).bfloat16()
+    aux = torch.randn(m, n, device="cuda", generator=g).bfloat16()
+    bias = torch.randn(n, device="cuda", generator=g)
+    ref = A.float() @ B.float().t() + bias
+    for rep in range(2):
+        out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+        cs = torch.zeros(n, device="cuda")
+        ops.gemm(A, B, m, n, k, out, bias=bias, epi=L.M3P_EPI_DROP_RES, aux=aux, drop_p=0.0, colsum=cs)
+        assert _rel(out, (ref + aux.float()).bfloat16()) < 1e-3, rep
+        assert float((cs - out.float().sum(0)).abs().max()) < 1e-3 * float(out.float().sum(0).abs().max())
+        out2 = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(A, B, m, n, k, out2, bias=bias)
+        assert _rel(out2, ref.bfloat16()) < 1e-3, rep
+
+
 def test_gemm_split_k_accumulates_fp32(m3p):
     from m3p_b200 import ops
     rows, n, k = 1000, 256, 128
