@@ -75,6 +75,74 @@ def pretrain_step(model, batch, sample_n=4, heads=("mlm", "mrm", "mrfr", "rel"),
     return total, losses
 
 
+def mask_out(x, lengths, n_words, pad_index=1, mask_index=None, word_pred=0.15, pred_probs=(0.8, 0.1, 0.1),
+             round_to=8, generator=None):
+    """Trainer.mask_out (xtrainer.py:385-434, the sample_alpha == 0 branch of the published recipes): choose
+    word_pred of the positions (never padding, never position 0), round the count down to a multiple of 8 as the
+    reference does for fp16 (:409-415), and replace each chosen token by <mask> / itself / a random token with
+    probabilities pred_probs.  Host-side batch preparation like the reference's (numpy there, torch here);
+    returns (x_masked, y, pred_mask) with y = the original tokens in (slen, bs) row-major order."""
+    slen, bs = x.shape
+    mask_index = n_words - 1 if mask_index is None else mask_index  # tokenization.py:79-81: <mask> is the last id
+    pred_mask = torch.rand(slen, bs, generator=generator) <= word_pred
+    pred_mask &= x.cpu() != pad_index
+    pred_mask[0] = False
+    flat = pred_mask.view(-1)
+    n1 = int(flat.sum())
+    if round_to > 1:
+        n2 = max(n1 % round_to, round_to * (n1 // round_to))
+        if n2 != n1:
+            flat[torch.nonzero(flat).view(-1)[:n1 - n2]] = False
+    if int(flat.sum()) == 0:
+        pred_mask[0, 0] = True
+    pred_mask = pred_mask.to(x.device)
+    x_real = x[pred_mask]
+    x_rand = torch.randint(0, n_words, x_real.shape, generator=generator).to(x.device)
+    probs = torch.multinomial(torch.tensor(pred_probs), len(x_real), replacement=True, generator=generator).to(x.device)
+    x_new = torch.where(probs == 0, torch.full_like(x_real, mask_index), torch.where(probs == 1, x_real, x_rand))
+    x = x.masked_scatter(pred_mask, x_new)
+    assert 0 <= int(x.min()) <= int(x.max()) < n_words
+    return x, x_real, pred_mask
+
+
+def mlm_step(model, x, lengths, pred_mask, y, positions=None, langs=None, lambda_coeff=1.0):
+    """Trainer.mlm_step (xtrainer.py:734-770), the xMLM / TLM objective: text stream through `crossfwd`
+    (+ language embeddings when `langs` is given), MLM head on the masked positions.  Inputs are what
+    `mask_out` returns, already on the device.  Returns lambda_coeff * loss."""
+    tensor = model("crossfwd", stream_="text", x=x, lengths=lengths, positions=positions, langs=langs, causal=False)
+    _, loss = model("predict", tensor=tensor, pred_mask=pred_mask, y=y, get_scores=False)
+    return lambda_coeff * loss
+
+
+def freelb_relation_step(model, batch, sample_n=4, adv_steps=3, adv_lr_text=1e-1, adv_lr_img=1e-1, max_norm=0.0):
+    """The FreeLB variant of the ITM fine-tune step (xtrainer.py:2021-2223, `--is_freelb`): `adv_steps` ascent
+    steps on perturbations of the token embeddings (`jointfwd(text_embed=...)`, :910-913) and of the region
+    features, accumulating the parameter gradients of every ascent step (averaged), as FreeLB does.  Uses the
+    input gradients d text_embed / d x_img the encoder backward provides.  Returns the mean loss."""
+    emb = model.embeddings.weight
+    x, R = batch["x"], batch["x_img"].shape[0]
+    base_text = torch.nn.functional.embedding(x.transpose(0, 1), emb.detach())        # (B, T, d) fp32
+    delta_t = torch.zeros_like(base_text)
+    delta_i = torch.zeros_like(batch["x_img"])
+    total = 0.0
+    for _ in range(adv_steps):
+        dt = delta_t.clone().requires_grad_(True)
+        di = delta_i.clone().requires_grad_(True)
+        enc = model("jointfwd", x=x, lengths=batch["lengths"], x_img=batch["x_img"] + di, lengths_img=batch["lengths_img"],
+                    causal=False, image_loc=batch["image_loc"], text_embed=base_text + dt)
+        scores = model("predict", tensor=enc.transpose(0, 1), is_relation=True)
+        loss = relation_loss(scores, batch["pos_labels"], sample_n) / adv_steps
+        loss.backward()          # parameter gradients accumulate in the flat buffer; dt.grad / di.grad for the ascent
+        total = total + float(loss.detach())
+        for d_, g_, lr in ((delta_t, dt.grad, adv_lr_text), (delta_i, di.grad, adv_lr_img)):
+            gn = g_.flatten(1).norm(dim=1).clamp_min(1e-12).view(-1, *([1] * (g_.dim() - 1)))
+            d_.add_(lr * g_ / gn)                                                    # normalised ascent step
+            if max_norm > 0:
+                dn = d_.flatten(1).norm(dim=1).view(-1, *([1] * (d_.dim() - 1)))
+                d_.mul_((max_norm / dn.clamp_min(1e-12)).clamp(max=1.0))
+    return total
+
+
 def synthetic_batch(B, T, R, n_words, sample_n=4, seed=1234, ragged=False, n_mask_text=16, n_mask_img=16,
                     device="cpu", feat_dim=2048):
     """Seeded synthetic batch in the layout and value distributions of the reference pipeline

@@ -755,3 +755,44 @@ def test_train_x_entry_trains_and_checkpoints(m3p, tmp_path, capsys):
     missing = fresh.load_state_dict(ck["model"], strict=False)
     assert not [k for k in missing.missing_keys if not k.startswith("refine_embeddings")]
     assert ck["params"]["emb_dim"] == 128
+
+
+def test_mlm_step_and_mask_out(m3p):
+    """xMLM step (xtrainer.py:734-770) through crossfwd + the MLM head with language embeddings, on a batch masked
+    by mask_out (:385-434): masked count is a multiple of 8, targets are the original tokens, loss matches the
+    oracle and trains."""
+    from m3p_b200 import optim
+    from m3p_b200.train_step import mask_out, mlm_step, synthetic_batch
+    from oracle import m3p_oracle as O
+    ns = _ns(128, 2, 2, 600, n_langs=3)
+    model = _model(m3p, ns)
+    b = synthetic_batch(8, 24, 2, ns.n_words, sample_n=4, seed=9, ragged=True)
+    g = torch.Generator().manual_seed(5)
+    x, y, pm = mask_out(b["x"], b["lengths"], ns.n_words, word_pred=0.3, generator=g)
+    assert int(pm.sum()) % 8 == 0 and int(pm.sum()) > 0 and not bool(pm[0].any())
+    assert torch.equal(y, b["x"][pm]) and not bool((b["x"][pm] == 1).any())
+    langs = torch.randint(0, 3, x.shape, generator=g)
+    xd, yd, pmd, ld, lg = x.cuda(), y.cuda(), pm.cuda(), b["lengths"].cuda(), langs.cuda()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    loss = mlm_step(model, xd, ld, pmd, yd, langs=lg)
+    ref_t = O.crossfwd_text(sd, ns.n_layers, ns.n_heads, xd, ld, langs=lg)
+    _, ref = O.predict_mlm(sd, ref_t, pmd, yd)
+    assert abs(float(loss.detach()) - float(ref)) < LOSS_TOL * abs(float(ref))
+    opt = optim.get_optimizer([p for p in model.parameters() if p.requires_grad], "adam,lr=0.003")
+    first = float(loss.detach())
+    for _ in range(8):
+        model.zero_grad()
+        loss = mlm_step(model, xd, ld, pmd, yd, langs=lg)
+        loss.backward()
+        opt.step()
+    assert float(loss.detach()) < first
+
+
+def test_freelb_relation_step_runs_and_accumulates(m3p):
+    from m3p_b200.train_step import freelb_relation_step, synthetic_batch
+    ns = _ns(128, 2, 2, 500)
+    model = _model(m3p, ns)
+    b = synthetic_batch(4, 12, 5, ns.n_words, sample_n=2, seed=2, device="cuda")
+    model.zero_grad()
+    loss = freelb_relation_step(model, b, sample_n=2, adv_steps=3)
+    assert loss == loss and float(model._flat_grad.abs().max()) > 0 and torch.isfinite(model._flat_grad).all()
