@@ -275,7 +275,8 @@ loc_wgrad_kernel(const __nv_bfloat16* __restrict__ de, const float* __restrict__
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
   float acc[5] = {0, 0, 0, 0, 0};
-  for (long long ir = r0; ir < r1; ++ir) {
+#pragma unroll 8
+  for (long long ir = r0; ir < r1; ++ir) {  // unrolled: 8 rows' loads in flight (the loop is latency-bound)
     const long long b = ir / R, s = ir % R;
     const float g = __bfloat162float(de[ir * d + j]);
     const float* l = image_loc + (s * B + b) * 5;
@@ -342,7 +343,7 @@ extern "C" int m3p_loc_wgrad(const void* de, const float* image_loc, float* dw_l
   M3P_REQUIRE(de && image_loc && dw_loc && B > 0 && R > 0 && d > 0, "m3p_loc_wgrad: bad arguments");
   const int gy = (int)((d + EMB_THREADS - 1) / EMB_THREADS);
   const long long rows = B * R;
-  int gx = sm_count() * 2 / gy;
+  int gx = sm_count() * 4 / gy;
   if (gx < 1) gx = 1;
   if (gx > rows) gx = (int)rows;
   const long long rpc = (rows + gx - 1) / gx;
