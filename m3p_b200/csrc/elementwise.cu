@@ -116,64 +116,45 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
   const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * EW_WARPS;
   const int nchunks = d >> 3;
-  // rows per warp iteration.  Two rows in flight per warp were measured SLOWER (430 vs 370 us per step: 80 registers
-  // -> 3 CTAs/SM instead of 4, and the grid already gives every warp at most two rows), so one row at a time it stays.
-  constexpr int NR = 1;
-  for (long long row0 = warp0; row0 < rows; row0 += NR * nwarps) {
-    Raw8<__nv_bfloat16> raw[NR][MAXC];
-    bool live[NR];
+  // (two rows in flight per warp were measured slower: 430 vs 370 us per step — more registers, 3 CTAs/SM instead of 4)
+  for (long long row = warp0; row < rows; row += nwarps) {
+    float v[MAXC][8];
+    float sum = 0.f;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const long long row = row0 + r * nwarps;
-      live[r] = row < rows;
+    for (int c = 0; c < MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
+        load8(x + row * d + ch * 8, v[c]);
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        const int ch = lane + 32 * c;
-        if (live[r] && ch < nchunks) raw[r][c].load(x + row * d + ch * 8);
+        for (int j = 0; j < 8; ++j) sum += v[c][j];
       }
     }
+    const float mean = warp_sum(sum) / d;
+    float sq = 0.f;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      if (!live[r]) continue;  // warp-uniform
-      const long long row = row0 + r * nwarps;
-      float v[MAXC][8];
-      float sum = 0.f;
+    for (int c = 0; c < MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        const int ch = lane + 32 * c;
-        if (ch < nchunks) {
-          raw[r][c].unpack(v[c]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sum += v[c][j];
-        }
+        for (int j = 0; j < 8; ++j) { const float t = v[c][j] - mean; sq += t * t; }
       }
-      const float mean = warp_sum(sum) / d;
-      float sq = 0.f;
-#pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        const int ch = lane + 32 * c;
-        if (ch < nchunks) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { const float t = v[c][j] - mean; sq += t * t; }
-        }
-      }
-      const float rstd = rsqrtf(warp_sum(sq) / d + eps);
-      bool valid = true;
-      if (seqlen != nullptr) valid = (row % S) < seqlen[row / S];
-#pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        const int ch = lane + 32 * c;
-        if (ch < nchunks) {
-          float g[8], b[8], o[8];
-          load8(gamma + ch * 8, g);
-          load8(beta + ch * 8, b);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = valid ? fmaf((v[c][j] - mean) * rstd, g[j], b[j]) : 0.f;
-          store8(y + row * d + ch * 8, o);
-        }
-      }
-      if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
     }
+    const float rstd = rsqrtf(warp_sum(sq) / d + eps);
+    bool valid = true;
+    if (seqlen != nullptr) valid = (row % S) < seqlen[row / S];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
+        float g[8], b[8], o[8];
+        load8(gamma + ch * 8, g);
+        load8(beta + ch * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = valid ? fmaf((v[c][j] - mean) * rstd, g[j], b[j]) : 0.f;
+        store8(y + row * d + ch * 8, o);
+      }
+    }
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
   }
 }
 
