@@ -154,7 +154,10 @@ def main(params):
         while seen < params.epoch_size:
             batch = host[n_iter % n_data]
             if graphed is not None:
-                loss = graphed.step(batch)
+                # pipelined feed: this batch was staged during the previous step; stage the next one now
+                if n_iter == 0:
+                    graphed.prefetch(batch)
+                loss = graphed.step_prefetched(host[(n_iter + 1) % n_data])
             else:
                 if n_iter % acc == 0:
                     model.zero_grad()

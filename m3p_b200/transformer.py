@@ -1056,8 +1056,15 @@ class _MlmFn(torch.autograd.Function):
             model._g("pred_layer.proj.bias")[(V // 8) * 8:] += dlog[:, (V // 8) * 8:V].float().sum(0)
         dt = None
         if ctx.needs_input_grad[0]:
+            # d rows = dlogits E: a [n x d] output (12 tiles of 256 x 256 for n = 1024) with K = V = 250 002 — without a
+            # K split 12 clusters would each run ~3 900 k-blocks while 62 idle; split K over the whole machine into an
+            # fp32 accumulator, then round once
+            drows32 = torch.zeros(n, d, dtype=_F32, device=dev)
+            tiles = ((n + 255) // 256) * ((d + 255) // 256)
+            ops.gemm(dlog, model._emb16, n, d, V, drows32, b_mn=True, out_f32=True, accumulate=True,
+                     split_k=max(1, min(32, 148 // max(tiles, 1))))
             drows = torch.empty(n, d, dtype=_BF16, device=dev)
-            ops.gemm(dlog, model._emb16, n, d, V, drows, b_mn=True)
+            ops.cast_f32_bf16(drows32, drows, n * d)
             dt = torch.zeros(slen, bs, d, dtype=_BF16, device=dev)
             ops.scatter_rows(drows, idx, bs, bs * d, d, dt, n, d)
         return dt, None, None, None, None, None

@@ -345,10 +345,11 @@ def test_crossfwd_image_stream_dropout_backward(m3p):
 # ---------------------------------------------------------------------------------------------------
 # against the oracle at M3P-base width (the oracle runs the same torch restatement, fp32, on the GPU)
 # ---------------------------------------------------------------------------------------------------
-def test_base_width_step_matches_oracle(m3p):
+@pytest.mark.parametrize("width,heads", [(768, 12), (1024, 16)])  # M3P-base and M3P-large (BASELINE configs[4]) widths
+def test_base_width_step_matches_oracle(m3p, width, heads):
     from m3p_b200.train_step import pretrain_step, synthetic_batch
     from oracle import m3p_oracle as O
-    ns = _ns(768, 2, 12, 3000)
+    ns = _ns(width, 2, heads, 3000)
     model = _model(m3p, ns)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     batch = synthetic_batch(8, 128, 100, ns.n_words, sample_n=4, seed=5, ragged=True, device="cuda")
