@@ -215,7 +215,7 @@ def main():
     B = args.batch
     torch.manual_seed(0)
     model = TransformerModel(namespace(CFG), is_encoder=True, with_output=True, is_crossModal=True).cuda().train()
-    reducer = GradReducer(model)
+    reducer = GradReducer(model, overlap=os.environ.get("M3P_DDP_OVERLAP", "1") != "0")
     host = synthetic_batch(B, CFG["T"], CFG["R"], CFG["n_words"], sample_n=CFG["sample_n"], seed=1234 + rank)
     host = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
