@@ -326,7 +326,11 @@ def main():
                                   "sustained cuBLAS bf16 peak, %s" % (gf, pk["source"]),
                          "dominant_kernel": {"name": "gemm_kernel<256, GELU> FFN lin1 14592x3072x768", "ms": dom_ms,
                                              "achieved": dom_tf, "peak": pk["burst"], "frac": dom_tf / pk["burst"],
-                                             "note": "timed alone, L2 flushed, vs burst peak"}},
+                                             "note": "timed alone, L2 flushed, vs burst peak",
+                                             "traffic": 152.4e6, "traffic_note": "dram__bytes_read+write per launch "
+                                             "(ncu --set full, profiles/r01_ncu_full_kernels.txt id 6: 27.3 MB read + "
+                                             "125.1 MB written; algorithmic 22.4 MB A + 4.7 MB W + 2 x 89.7 MB outputs, "
+                                             "part of which is still in L2 when the kernel ends)"}},
         }
     if world > 1:
         dist.barrier()

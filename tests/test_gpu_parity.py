@@ -797,3 +797,33 @@ def test_freelb_relation_step_runs_and_accumulates(m3p):
     model.zero_grad()
     loss = freelb_relation_step(model, b, sample_n=2, adv_steps=3)
     assert loss == loss and float(model._flat_grad.abs().max()) > 0 and torch.isfinite(model._flat_grad).all()
+
+
+def test_retrieval_evaluation_scores_match_oracle(m3p):
+    """Forward-only retrieval evaluation (xevaluator.py:1528-1657): every (image, caption) ITM score through
+    jointfwd + predict(is_relation) in eval mode equals the oracle's, and recall@k is counted like the reference."""
+    from m3p_b200.evaluate import evaluate_image_retrieval, matching_scores, recall_at_k
+    from m3p_b200.train_step import synthetic_batch
+    from oracle import m3p_oracle as O
+    ns = _ns(128, 2, 2, 500, dropout=0.1)  # dropout must be inert in eval mode
+    model = _model(m3p, ns)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    n_img, spi, T, R = 3, 2, 10, 4
+    b = synthetic_batch(n_img * spi, T, R, ns.n_words, sample_n=2, seed=4, ragged=True, device="cuda")
+    x_img, loc = b["x_img"][:, :n_img].contiguous(), b["image_loc"][:, :n_img].contiguous()
+    scores = matching_scores(model, x_img, loc, b["x"], b["lengths"], pairs_per_call=4)
+    assert model.training  # restored
+    ref = torch.empty_like(scores)
+    for i in range(n_img):
+        n = n_img * spi
+        enc = O.jointfwd(sd, ns.n_layers, ns.n_heads, b["x"], b["lengths"], x_img[:, i:i + 1].expand(R, n, -1),
+                         torch.full((n,), R, device="cuda"), loc[:, i:i + 1].expand(R, n, -1))
+        ref[i] = O.predict_relation(sd, enc.transpose(0, 1)).view(-1)
+    assert _rel(scores, ref) < OUT_TOL
+    out = evaluate_image_retrieval(model, x_img, loc, b["x"], b["lengths"], seq_per_img=spi, pairs_per_call=4)
+    assert len(out) == 6 and all(0.0 <= v <= 1.0 for v in out)
+    # recall bookkeeping on a hand-made score matrix: image 0 ranks its caption first, image 1 third
+    sc = torch.tensor([[0.9, 0.1, 0.2, 0.0], [0.8, 0.7, 0.1, 0.6]], device="cuda")
+    lab = torch.tensor([[1, 0, 0, 0], [0, 0, 0, 1]], device="cuda")
+    i2t, t2i = recall_at_k(sc, lab, ks=(1, 2, 3))
+    assert i2t == {1: 0.5, 2: 0.5, 3: 1.0} and t2i[1] == 0.5  # captions 1, 2 belong to no image here
