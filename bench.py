@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GF_PER_PAIR = {"itm": 122.886, "multitask": 143.356}  # BASELINE.md §3 (matmul FLOPs, fwd+bwd = 3x fwd)
+GF_PER_PAIR_LARGE = {"itm": 429.714, "multitask": 457.167}  # SURVEY.md §8d, M3P-large 24L/1024H (BASELINE configs[4])
 HEADS = {"itm": ("rel",), "multitask": ("mlm", "mrm", "mrfr", "rel")}
 CFG = dict(emb_dim=768, n_layers=12, n_heads=12, n_words=250002, T=128, R=100, sample_n=4, dropout=0.1)
 CPU_SAMPLE_PAIRS = 4
@@ -155,7 +156,8 @@ def run_reference(args):
 
 def workload_name(heads):
     h = "ITM head (t2i/i2t fine-tune step)" if heads == "itm" else "xMLM-style MLM + MRM + MRFR + ITM heads (multitask step)"
-    return "M3P-base 12L/768H/12h jointfwd fwd+bwd, 100 regions + 128 tokens, 64 pairs/GPU, " + h
+    return "M3P-%s %dL/%dH/%dh jointfwd fwd+bwd, 100 regions + 128 tokens, 64 pairs/GPU, " % (
+        "base" if CFG["emb_dim"] == 768 else "large", CFG["n_layers"], CFG["emb_dim"], CFG["n_heads"]) + h
 
 
 def time_dominant_kernel(torch, ops, L):
@@ -190,10 +192,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--heads", default="itm", choices=["itm", "multitask"])
     ap.add_argument("--batch", type=int, default=64, help="pairs per GPU")
+    ap.add_argument("--model", default="base", choices=["base", "large"],
+                    help="base = the headline M3P-base workload; large = BASELINE configs[4] (24L/1024H/16 heads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.model == "large":
+        CFG.update(emb_dim=1024, n_layers=24, n_heads=16)
+        GF_PER_PAIR.update(GF_PER_PAIR_LARGE)
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its banner there)
     if args.impl == "reference":
@@ -305,7 +312,7 @@ def main():
     if rank == 0:
         dom_tf, dom_ms = time_dominant_kernel(torch, ops, L)
         out = {
-            "metric": "image-text pairs/sec fwd+bwd, M3P-base 228-tok seq", "value": value, "unit": "pairs/s",
+            "metric": "image-text pairs/sec fwd+bwd, M3P-%s 228-tok seq" % args.model, "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args.heads), "global_batch": B * world, "seq_len": CFG["T"] + CFG["R"],
