@@ -47,7 +47,7 @@ constexpr uint32_t SLAB_BYTES = 64 * BLOCK_K * 2;  // one 64-wide MN slab of an 
 
 struct GemmKernelParams {
   int M, N, K;
-  int num_n_tiles, split_k, num_units;
+  int num_n_tiles, num_m_tiles, m_fastest, split_k, num_units;
   int kblocks_total, kblocks_per_split;
   int a_mn, b_mn;
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
@@ -69,12 +69,22 @@ struct GemmKernelParams {
   float* colsum;  // optional [N]: += column sums of the stored (bf16-rounded) output
 };
 
+// Unit order: K split fastest, then the tile dimension with FEWER tiles.  Units that are adjacent in this order
+// run concurrently on neighbouring clusters, so the operand tile they share is fetched from HBM once and hit in
+// L2 by the others; the operand indexed by the slower dimension is re-read once per wave.  Making the short
+// dimension fast keeps the sharers of the LARGE operand together (FFN lin2 wgrad, 3 x 12 tiles: 214 -> ~134 MB of
+// DRAM reads per launch).
 __device__ __forceinline__ void decode_unit(const GemmKernelParams& p, int u, int& m_tile,
                                             int& n_tile, int& ks) {
   ks = u % p.split_k;
   const int t = u / p.split_k;
-  n_tile = t % p.num_n_tiles;
-  m_tile = t / p.num_n_tiles;
+  if (p.m_fastest) {
+    m_tile = t % p.num_m_tiles;
+    n_tile = t / p.num_m_tiles;
+  } else {
+    n_tile = t % p.num_n_tiles;
+    m_tile = t / p.num_n_tiles;
+  }
 }
 
 // ---- epilogue math on one 16-column chunk held by one thread (one output row) -------------------
@@ -712,6 +722,8 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   p.M = (int)a->m; p.N = (int)a->n; p.K = (int)a->k;
   const int num_m_tiles = (p.M + tile_m - 1) / tile_m;
   p.num_n_tiles = (p.N + BN - 1) / BN;
+  p.num_m_tiles = num_m_tiles;
+  p.m_fastest = num_m_tiles < p.num_n_tiles ? 1 : 0;
   p.kblocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   int split = a->split_k < p.kblocks_total ? a->split_k : p.kblocks_total;
   p.kblocks_per_split = (p.kblocks_total + split - 1) / split;
