@@ -24,9 +24,12 @@ class GradReducer:
         self._works = []
         self._done = set()
         self._post = []
+        self._dense_sent = False
         self._gather = {}  # persistent (all_ids, all_rows) buffers of the row-sparse exchange, keyed by size
         self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"  # gloo has no AVG: SUM then scale
         model._grad_ready_hook = self._segment_ready if self.world > 1 else None
+        model._defer_token_grads = self.world > 1 and overlap
+        self._dense_sent = False
 
     def _allreduce(self, buf):
         if self._avg:
@@ -43,6 +46,13 @@ class GradReducer:
         buf = self.model._flat_grad[lo:hi]
         if self.overlap:
             self._allreduce(buf)
+            m = self.model
+            if name == "heads" and getattr(m, "_emb_dense_dirty", False) and getattr(m, "_defer_token_grads", False) \
+                    and m._proj_grad is not None and not self._dense_sent:
+                # the MLM head has just added its dense V x d contribution (68 % of all gradient bytes): send it now,
+                # underneath the whole encoder backward; the embedding gather's rows follow in finish()
+                self._allreduce(m._proj_grad)
+                self._dense_sent = True
 
     def _exchange_embedding_rows(self, m, touched):
         """Row-sparse average of the token-embedding gradient.  Without the MLM head only the rows of the
@@ -69,6 +79,28 @@ class GradReducer:
         g.index_add_(0, all_ids, all_rows)
         m._emb_touched = [all_ids]  # what the next zero_grad has to clear
 
+    def _exchange_deferred_rows(self, m, deferred):
+        """Tied MLM head under data parallelism: the dense part of d E is already in flight; the embedding
+        gather's contribution was kept per token position (B, T, d).  All ranks all-gather (ids, rows / world) and
+        add every rank's rows into the (by then averaged) dense buffer: sum_r (dense_r + gather_r) / world."""
+        g = m._emb_grad
+        ids = torch.cat([x.t().reshape(-1) for x, _ in deferred])                  # batch-major, like the rows
+        rows = torch.cat([gp.reshape(-1, g.shape[1]) for _, gp in deferred])
+        rows = rows * ((ids != m.pad_index).to(rows.dtype) / self.world).unsqueeze(1)  # padding_idx gets no gradient
+        key = ("deferred", self.world * ids.numel(), g.shape[1], g.dtype, ids.device)
+        if key not in self._gather:
+            self._gather[key] = (torch.empty(key[1], dtype=ids.dtype, device=ids.device),
+                                 torch.empty(key[1], key[2], dtype=g.dtype, device=g.device))
+        all_ids, all_rows = self._gather[key]
+        dist.all_gather_into_tensor(all_ids, ids, group=self.group)
+        dist.all_gather_into_tensor(all_rows, rows, group=self.group)
+        for w in self._works:
+            w.wait()  # the dense all-reduce (and everything else in flight) has landed on the current stream
+        for buf in self._post:
+            buf.div_(self.world)
+        self._works, self._post = [], []
+        g.index_add_(0, all_ids, all_rows)
+
     def finish(self):
         """Call after backward(): reduces whatever has not been sent yet and joins the NCCL stream."""
         m = self.model
@@ -89,13 +121,24 @@ class GradReducer:
                 for lo, hi in rest:
                     self._allreduce(m._flat_grad[lo:hi])
                 touched = getattr(m, "_emb_touched", None)
-                if touched and not getattr(m, "_emb_dense_dirty", True):
-                    self._exchange_embedding_rows(m, touched)
+                deferred, m._deferred_token_grads = getattr(m, "_deferred_token_grads", []), []
+                if self._dense_sent:
+                    if m._proj_grad is not m._emb_grad:     # untied: the projection went early, the table as usual
+                        if touched and not m._emb_dense_dirty:
+                            self._exchange_embedding_rows(m, touched)
+                        else:
+                            self._allreduce(m._emb_grad)
+                    elif deferred:
+                        self._exchange_deferred_rows(m, deferred)
+                    m._emb_dense_dirty = True
                 else:
-                    self._allreduce(m._emb_grad)
-                    m._emb_dense_dirty = True  # rows touched by OTHER ranks are now non-zero here too
-                if m._proj_grad is not None and m._proj_grad is not m._emb_grad:
-                    self._allreduce(m._proj_grad)
+                    if touched and not getattr(m, "_emb_dense_dirty", True):
+                        self._exchange_embedding_rows(m, touched)
+                    else:
+                        self._allreduce(m._emb_grad)
+                        m._emb_dense_dirty = True  # rows touched by OTHER ranks are now non-zero here too
+                    if m._proj_grad is not None and m._proj_grad is not m._emb_grad:
+                        self._allreduce(m._proj_grad)
             for w in self._works:
                 w.wait()  # current stream waits for NCCL's
             for buf in self._post:
@@ -103,6 +146,7 @@ class GradReducer:
         self._works = []
         self._done = set()
         self._post = []
+        self._dense_sent = False
 
 
 def init_distributed():

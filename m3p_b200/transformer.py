@@ -112,6 +112,8 @@ class TransformerModel(nn.Module):
         self._device_checked = False
         self._emb_touched = None      # token-id tensors scattered into _emb_grad since it was last cleared
         self._emb_dense_dirty = True  # True once a dense update (tied MLM head) or foreign writer touched it
+        self._defer_token_grads = False      # set by ddp.GradReducer (world > 1): see _encode_backward
+        self._deferred_token_grads = []      # [(token ids (T,B), per-position gradient (B,T,d) fp32)]
         self.overlap_grads = os.environ.get("M3P_SIDE_STREAM", "1") != "0"
         self._side_streams = {}
         # set by m3p_b200.optim after a fused step (which also writes the bf16 operand copies and zeroes the
@@ -744,6 +746,13 @@ class TransformerModel(nn.Module):
             if want_dtext:
                 d_text = e(B, T, d, dt=_F32)
                 b.d_text_embed = d_text.data_ptr()
+            elif self._defer_token_grads and self._emb_dense_dirty and "positions" not in st:
+                # data-parallel step with the tied MLM head: the dense head contribution to d E is already being
+                # all-reduced (ddp.GradReducer sent it when the heads finished), so the gather's contribution must not
+                # be scattered into that buffer now — keep it per position and let the reducer exchange it as rows
+                g_pos = e(B, T, d, dt=_F32)
+                b.d_text_embed = g_pos.data_ptr()
+                self._deferred_token_grads.append((st["x"], g_pos))
             else:
                 b.d_tok_emb = self._emb_grad.data_ptr()
                 if self._emb_touched is not None:

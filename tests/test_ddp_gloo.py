@@ -66,6 +66,52 @@ def _worker_sparse(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_deferred(rank, world, port, q):
+    """Tied MLM head: the dense head contribution is all-reduced when the heads finish, the embedding gather's
+    per-position rows are exchanged at the end; the sum must equal the dense average of (head + gather) grads."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from m3p_b200.ddp import GradReducer
+    m = _FakeModel(rank)
+    V, d, T, B = 50, 8, 5, 3
+    m.pad_index = 1
+    g = torch.Generator().manual_seed(200 + rank)
+    head = torch.randn(V, d, generator=g)                   # dense dE from the MLM head
+    x = torch.randint(0, V, (T, B), generator=g)
+    x[-1, 0] = 1                                            # a padding token: must receive nothing
+    g_pos = torch.randn(B, T, d, generator=g)               # per-position gradient of the gather, batch-major
+    full = head.clone()
+    keep = (x.t().reshape(-1) != 1).float().unsqueeze(1)
+    full.index_add_(0, x.t().reshape(-1), g_pos.reshape(-1, d) * keep)
+    dense = [torch.zeros(V, d) for _ in range(world)]
+    dist.all_gather(dense, full)
+    want = sum(dense) / world
+    m._emb_grad = head.clone()
+    m._proj_grad = m._emb_grad
+    m._emb_dense_dirty = True
+    red = GradReducer(m)
+    assert m._defer_token_grads
+    m._grad_ready_hook("heads", *m._segments["heads"])      # dense part goes out here
+    m._deferred_token_grads = [(x, g_pos)]                  # what _encode_backward leaves behind
+    red.finish()
+    ok = torch.allclose(m._emb_grad, want, atol=1e-5) and m._emb_dense_dirty and not m._deferred_token_grads
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_deferred_token_rows_after_early_dense_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_deferred, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
+
 def test_row_sparse_embedding_exchange_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

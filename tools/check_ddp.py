@@ -12,7 +12,7 @@ import torch.distributed as dist  # noqa: E402
 
 import bench  # noqa: E402
 from m3p_b200.ddp import GradReducer, init_distributed  # noqa: E402
-from m3p_b200.train_step import pretrain_step, synthetic_batch  # noqa: E402
+from m3p_b200.train_step import prepare_batch, pretrain_step, synthetic_batch  # noqa: E402
 from m3p_b200.transformer import TransformerModel  # noqa: E402
 
 rank, local, world = init_distributed()
@@ -27,38 +27,43 @@ full = synthetic_batch(B * world, cfg["T"], cfg["R"], cfg["n_words"], sample_n=4
 def shard(lo, hi):
     out = {}
     for k, v in full.items():
-        if k in ("x", "x_img", "image_loc", "x_labels", "pred_mask_text"):
+        if k in ("x", "x_img", "image_loc", "x_labels"):
             out[k] = v[:, lo:hi].contiguous()
         elif k == "pos_labels":
             out[k] = v[lo // 4:hi // 4]
         elif k in ("lengths", "lengths_img", "obj_labels", "ori_feats"):
             out[k] = v[lo:hi]
-    return out
+    return prepare_batch(out)  # y_text / pred_mask_text / mrfr_weight of THIS shard (local means)
 
 
 mine = shard(rank * B, (rank + 1) * B)
-total, _ = pretrain_step(model, mine, 4, heads=("rel",))
-total.backward()
-reducer.finish()
-torch.cuda.synchronize()
-dp_flat, dp_emb = model._flat_grad.clone(), model._emb_grad.clone()
-# reference: every shard on this rank, no communication, mean of the per-shard gradients
-model._grad_ready_hook = None
-acc_flat, acc_emb = torch.zeros_like(dp_flat), torch.zeros_like(dp_emb)
-for r in range(world):
+for heads in (("rel",), ("mlm", "mrm", "mrfr", "rel")):
+    model._grad_ready_hook = reducer._segment_ready
+    model._defer_token_grads = True
     model.zero_grad()
-    t, _ = pretrain_step(model, shard(r * B, (r + 1) * B), 4, heads=("rel",))
-    t.backward()
-    acc_flat += model._flat_grad
-    acc_emb += model._emb_grad
-acc_flat /= world
-acc_emb /= world
-e1 = float((dp_flat - acc_flat).norm() / acc_flat.norm())
-e2 = float((dp_emb - acc_emb).norm() / acc_emb.norm())
-res = torch.tensor([e1, e2], device="cuda")
-dist.all_reduce(res, op=dist.ReduceOp.MAX)
-if rank == 0:
-    print(json.dumps({"case": "ddp_vs_single", "world": world, "flat_rel_err": float(res[0]), "emb_rel_err": float(res[1]),
-                      "ok": float(res.max()) < 2e-3}), flush=True)
+    total, _ = pretrain_step(model, mine, 4, heads=heads)
+    total.backward()
+    reducer.finish()
+    torch.cuda.synchronize()
+    dp_flat, dp_emb = model._flat_grad.clone(), model._emb_grad.clone()
+    # reference: every shard on this rank, no communication, mean of the per-shard gradients
+    model._grad_ready_hook = None
+    model._defer_token_grads = False
+    acc_flat, acc_emb = torch.zeros_like(dp_flat), torch.zeros_like(dp_emb)
+    for r in range(world):
+        model.zero_grad()
+        t, _ = pretrain_step(model, shard(r * B, (r + 1) * B), 4, heads=heads)
+        t.backward()
+        acc_flat += model._flat_grad
+        acc_emb += model._emb_grad
+    acc_flat /= world
+    acc_emb /= world
+    e1 = float((dp_flat - acc_flat).norm() / acc_flat.norm())
+    e2 = float((dp_emb - acc_emb).norm() / acc_emb.norm())
+    res = torch.tensor([e1, e2], device="cuda")
+    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"case": "ddp_vs_single", "heads": list(heads), "world": world, "flat_rel_err": float(res[0]),
+                          "emb_rel_err": float(res[1]), "ok": float(res.max()) < 2e-3}), flush=True)
 dist.barrier()
 dist.destroy_process_group()
