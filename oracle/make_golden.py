@@ -138,6 +138,18 @@ def run_optimizer_case(seed=3, n=1003, steps=6, max_norm=5.0):
         out["grads"].append(grads)
         out["norms"].append(float(norm))
         out["params"].append([p.detach().clone() for p in params])
+    # learning-rate schedules of the reference classes (pure Python: get_lr_for_step), optim.py:129-133, 184-201
+    from src.optim import AdamCosineWithWarmup
+    dummy = [torch.nn.Parameter(torch.zeros(1))]
+    inv = AdamInverseSqrtWithWarmup(dummy, lr=1e-4, warmup_updates=4000, warmup_init_lr=1e-7)
+    cos1 = AdamCosineWithWarmup(dummy, lr=1e-4, warmup_updates=100, warmup_init_lr=1e-7, min_lr=1e-9, init_period=500,
+                                period_mult=1, lr_shrink=0.75)
+    cos2 = AdamCosineWithWarmup(dummy, lr=1e-4, warmup_updates=100, warmup_init_lr=1e-7, min_lr=1e-9, init_period=300,
+                                period_mult=2, lr_shrink=0.5)
+    steps_ = [0, 1, 50, 99, 100, 101, 399, 400, 401, 777, 1000, 3999, 4000, 4001, 10000, 123456]
+    out["schedules"] = {"steps": steps_, "inverse_sqrt": [inv.get_lr_for_step(n) for n in steps_],
+                        "cosine_mult1": [cos1.get_lr_for_step(n) for n in steps_],
+                        "cosine_mult2": [cos2.get_lr_for_step(n) for n in steps_]}
     return out
 
 

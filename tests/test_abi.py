@@ -89,3 +89,59 @@ def test_train_x_parser_mirrors_reference_flags():
     ns = train_x.model_namespace(p)
     assert (ns.emb_dim, ns.n_layers, ns.n_heads, ns.n_words, ns.pad_index, ns.eos_index) == (1024, 24, 16, 250002, 1, 2)
     assert p.accumulate_gradients == 4 and p.clip_grad_norm == 5
+
+
+# ---------------------------------------------------------------------------------------------------
+# host logic that needs no GPU: optimizer DSL and schedules, batch masking, retrieval bookkeeping
+# ---------------------------------------------------------------------------------------------------
+def test_optimizer_dsl_and_schedules_match_the_reference(golden_dir):
+    """get_optimizer's string DSL (optim.py:211-270) and the LR schedules of AdamInverseSqrtWithWarmup /
+    AdamCosineWithWarmup (:129-133, :184-201) against values produced by the reference classes."""
+    import torch
+    from m3p_b200 import optim
+    g = torch.load(os.path.join(golden_dir, "adam_inverse_sqrt.pt"), weights_only=False)["schedules"]
+    p = [torch.nn.Parameter(torch.zeros(4))]
+    o = optim.get_optimizer(p, "adam_inverse_sqrt,beta1=0.9,beta2=0.98,lr=0.0001", clip_grad_norm=5.0)
+    assert isinstance(o, optim.AdamInverseSqrtWithWarmup) and o.param_groups[0]["betas"] == (0.9, 0.98)
+    assert o.clip_grad_norm == 5.0 and o.param_groups[0]["lr"] == 1e-7 and o.param_groups[0]["num_updates"] == 0
+    for n, want in zip(g["steps"], g["inverse_sqrt"]):
+        assert abs(o.get_lr_for_step(n) - want) <= 1e-12 * max(1.0, abs(want)) + 1e-18
+    c1 = optim.get_optimizer(p, "adam_cosine,lr=0.0001,warmup_updates=100,min_lr=0.000000001,init_period=500,lr_shrink=0.75")
+    c2 = optim.AdamCosineWithWarmup(p, lr=1e-4, warmup_updates=100, warmup_init_lr=1e-7, min_lr=1e-9, init_period=300,
+                                    period_mult=2, lr_shrink=0.5)
+    for n, w1, w2 in zip(g["steps"], g["cosine_mult1"], g["cosine_mult2"]):
+        assert abs(c1.get_lr_for_step(n) - w1) <= 1e-9 * abs(w1) + 1e-18
+        assert abs(c2.get_lr_for_step(n) - w2) <= 1e-9 * abs(w2) + 1e-18
+    a = optim.get_optimizer(p, "adam,lr=0.001")
+    assert type(a) is optim.Adam and a.param_groups[0]["lr"] == 0.001
+    with pytest.raises(NotImplementedError):
+        optim.get_optimizer(p, "sgd,lr=0.1")          # torch.optim pass-throughs are outside the B200 path
+    with pytest.raises(Exception):
+        optim.get_optimizer(p, "adam,momentum=0.9")   # unexpected parameter, as the reference rejects it
+    with pytest.raises(Exception):
+        optim.get_optimizer(p, "nadam")
+
+
+def test_mask_out_follows_the_reference_rules():
+    """Trainer.mask_out (xtrainer.py:385-434): never position 0 or padding, count rounded down to a multiple of 8,
+    targets are the original tokens, replacements are <mask> / same / random in roughly 80/10/10."""
+    import torch
+    from m3p_b200.train_step import mask_out, synthetic_batch
+    b = synthetic_batch(32, 64, 2, 1000, sample_n=4, seed=1, ragged=True)
+    g = torch.Generator().manual_seed(0)
+    x, y, pm = mask_out(b["x"], b["lengths"], 1000, word_pred=0.15, generator=g)
+    n = int(pm.sum())
+    assert n > 0 and n % 8 == 0 and not bool(pm[0].any()) and not bool((b["x"][pm] == 1).any())
+    assert torch.equal(y, b["x"][pm]) and torch.equal(x[~pm], b["x"][~pm])
+    frac_mask = float((x[pm] == 999).float().mean())
+    frac_same = float((x[pm] == y).float().mean())
+    assert 0.65 < frac_mask < 0.92 and 0.03 < frac_same < 0.25
+
+
+def test_recall_at_k_counts_like_the_reference():
+    import torch
+    from m3p_b200.evaluate import recall_at_k
+    sc = torch.tensor([[0.9, 0.1, 0.2, 0.0], [0.8, 0.7, 0.1, 0.6]])
+    lab = torch.tensor([[1, 0, 0, 0], [0, 0, 0, 1]])
+    i2t, t2i = recall_at_k(sc, lab, ks=(1, 2, 3))
+    assert i2t == {1: 0.5, 2: 0.5, 3: 1.0} and t2i == {1: 0.5, 2: 0.5, 3: 0.5}
