@@ -39,13 +39,9 @@ int get_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t 
                      uint64_t dim2, uint64_t pitch1, uint64_t pitch2, uint32_t box0, uint32_t box1,
                      uint32_t box2);
 int sm_count();
-// Library-owned scratch for cross-CTA partial sums (column reductions of LayerNorm / bias gradients):
-// one buffer per process (= per GPU), grown on demand, reused by every call on the stream.  Many CTAs
-// adding atomically into the same few thousand addresses serialise in L2 (~250 cycles per same-address
-// op measured on B200), so reductions go partials -> scratch -> one small second-stage kernel instead.
+// Library-owned scratch (per-row losses of the cross-entropy kernels): one buffer per process (= per GPU),
+// grown on demand, reused by every call on the stream.
 float* scratch_f32(size_t n_floats);
-// out_k[col] += sum_p partial[p][k * seg + col]  for k < nout; second stage of the reductions above.
-int reduce_partials(const float* partial, int parts, int seg, float* const* outs, int nout, cudaStream_t stream);
 
 // Device word XOR-ed into every dropout seed at kernel start (m3p_set_seed_mix): lets a captured CUDA graph
 // replay with fresh masks — the caller bumps the word between replays, the launch parameters stay constant.

@@ -70,40 +70,6 @@ static int ew_grid(long long rows) {
 }
 
 // =================================================================================================
-// second stage of the column reductions: out_k[col] += sum_p partial[p][k*seg + col]
-// =================================================================================================
-struct ReduceOuts { float* p[4]; };
-__global__ void __launch_bounds__(EW_THREADS)
-reduce_partials_kernel(const float* __restrict__ partial, int parts, int seg, int ncols, ReduceOuts outs) {
-  const int col = blockIdx.x * EW_THREADS + threadIdx.x;
-  if (col >= ncols) return;
-  float* dst = outs.p[col / seg];
-  if (dst == nullptr) return;
-  float acc = 0.f;
-  int p = blockIdx.y;
-  const int step = gridDim.y;
-  for (; p + 3 * step < parts; p += 4 * step) {
-    const float a = partial[(long long)p * ncols + col], b = partial[(long long)(p + step) * ncols + col];
-    const float c = partial[(long long)(p + 2 * step) * ncols + col], e = partial[(long long)(p + 3 * step) * ncols + col];
-    acc += (a + b) + (c + e);
-  }
-  for (; p < parts; p += step) acc += partial[(long long)p * ncols + col];
-  atomicAdd(dst + (col % seg), acc);  // gridDim.y-way contention only
-}
-
-int reduce_partials(const float* partial, int parts, int seg, float* const* outs, int nout, cudaStream_t stream) {
-  ReduceOuts o{};
-  for (int i = 0; i < nout && i < 4; ++i) o.p[i] = outs[i];
-  const int ncols = seg * nout;
-  int gy = parts / 16;
-  gy = gy < 1 ? 1 : (gy > 8 ? 8 : gy);
-  reduce_partials_kernel<<<dim3((ncols + EW_THREADS - 1) / EW_THREADS, gy), EW_THREADS, 0, stream>>>(partial, parts, seg,
-                                                                                                   ncols, o);
-  M3P_CUDA_OK(cudaGetLastError());
-  return M3P_OK;
-}
-
-// =================================================================================================
 // LayerNorm forward:  y = mask * ((x - mean) * rstd * gamma + beta)      transformer.py:953,957-958
 // =================================================================================================
 template <int MAXC>
@@ -175,7 +141,6 @@ struct LnBwdParams {
   uint32_t dy_thr16, dy_seed_lo, dy_seed_hi; float dy_scale;
   const uint64_t* seed_mix;
   float* dgamma; float* dbeta; float* dbias;
-  float* partial;  // [gridDim.x][3][d] scratch: per-CTA column sums (dgamma | dbeta | dbias)
   long long rows; int d;
 };
 

@@ -269,6 +269,8 @@ class GraphedStep:
 
     def step_prefetched(self, next_host_batch=None):
         """Run one step on the batch staged by the last `prefetch()`, and start prefetching `next_host_batch`."""
+        if not hasattr(self, "_staged_ready"):
+            raise RuntimeError("step_prefetched() needs a batch staged by prefetch() first")
         cur = torch.cuda.current_stream()
         cur.wait_event(self._staged_ready)
         for k in self._staged_keys:
