@@ -150,111 +150,119 @@ class Adam(torch.optim.Optimizer):
         self.n_steps = int(sd.get("n_steps", 0))
 
 
-class AdamInverseSqrtWithWarmup(Adam):
-    """optim.py:89-139: linear warm-up from warmup_init_lr to lr over warmup_updates, then
-    lr * sqrt(warmup_updates) / sqrt(num_updates) (exp_factor 0.5)."""
+# ---- learning-rate schedules: pure functions of the update count (the classes below only hold their settings) ----
+
+def warmup_lr(n, init_lr, peak_lr, warmup):
+    """Linear ramp init_lr -> peak_lr over `warmup` updates (both reference schedules start with it)."""
+    return init_lr + n * (peak_lr - init_lr) / warmup
+
+
+def inverse_sqrt_lr(n, peak_lr, warmup, init_lr=1e-7, exponent=0.5):
+    """optim.py:129-133: after the ramp, peak_lr * (warmup / n) ** exponent."""
+    if n < warmup:
+        return warmup_lr(n, init_lr, peak_lr, warmup)
+    return peak_lr * warmup ** exponent * n ** (-exponent)
+
+
+def cosine_lr(n, peak_lr, warmup, init_lr=1e-7, floor_lr=1e-9, period=1000000, growth=1, shrink=0.75):
+    """optim.py:184-201: after the ramp, cosine cycles; cycle c lasts period * growth**c updates and runs between
+    floor_lr * shrink**c and peak_lr * shrink**c."""
+    if n < warmup:
+        return warmup_lr(n, init_lr, peak_lr, warmup)
+    t = n - warmup
+    if growth == 1:
+        cycle = math.floor(t / period)
+        length, into = period, t - period * cycle
+    else:
+        cycle = math.floor(math.log(1 - t / period * (1 - growth), growth))
+        length = period * growth ** cycle
+        into = t - (1 - growth ** cycle) / (1 - growth) * period
+    lo, hi = floor_lr * shrink ** cycle, peak_lr * shrink ** cycle
+    return lo + 0.5 * (hi - lo) * (1 + math.cos(math.pi * into / length))
+
+
+class _ScheduledAdam(Adam):
+    """Adam whose param_groups carry `num_updates` and get a new `lr` after every step (optim.py:135-139, 203-208)."""
+
+    def __init__(self, params, start_lr, **kw):
+        super().__init__(params, lr=start_lr, **kw)
+        for group in self.param_groups:
+            group["num_updates"] = 0
+
+    def get_lr_for_step(self, num_updates):
+        raise NotImplementedError
+
+    def step(self, closure=None):
+        loss = super().step(closure)
+        for group in self.param_groups:
+            group["num_updates"] += 1
+            group["lr"] = self.get_lr_for_step(group["num_updates"])
+        return loss
+
+
+class AdamInverseSqrtWithWarmup(_ScheduledAdam):
+    """optim.py:89-139 (same constructor arguments)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, warmup_updates=4000,
                  warmup_init_lr=1e-7, exp_factor=0.5, **kw):
-        super().__init__(params, lr=warmup_init_lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)
-        self.warmup_updates = warmup_updates
-        self.warmup_init_lr = warmup_init_lr
-        warmup_end_lr = lr
-        self.lr_step = (warmup_end_lr - warmup_init_lr) / warmup_updates
-        self.exp_factor = exp_factor
-        self.decay_factor = warmup_end_lr * warmup_updates ** self.exp_factor
-        for param_group in self.param_groups:
-            param_group['num_updates'] = 0
+        super().__init__(params, warmup_init_lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)
+        self.peak_lr, self.warmup_updates, self.warmup_init_lr, self.exp_factor = lr, warmup_updates, warmup_init_lr, exp_factor
 
     def get_lr_for_step(self, num_updates):
-        if num_updates < self.warmup_updates:
-            return self.warmup_init_lr + num_updates * self.lr_step
-        return self.decay_factor * (num_updates ** -self.exp_factor)
-
-    def step(self, closure=None):
-        loss = super().step(closure)
-        for param_group in self.param_groups:
-            param_group['num_updates'] += 1
-            param_group['lr'] = self.get_lr_for_step(param_group['num_updates'])
-        return loss
+        return inverse_sqrt_lr(num_updates, self.peak_lr, self.warmup_updates, self.warmup_init_lr, self.exp_factor)
 
 
-class AdamCosineWithWarmup(Adam):
-    """optim.py:142-208: linear warm-up, then cosine cycles with period growth and per-cycle shrink."""
+class AdamCosineWithWarmup(_ScheduledAdam):
+    """optim.py:142-208 (same constructor arguments)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, warmup_updates=4000,
                  warmup_init_lr=1e-7, min_lr=1e-9, init_period=1000000, period_mult=1, lr_shrink=0.75, **kw):
-        super().__init__(params, lr=warmup_init_lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)
-        self.warmup_updates = warmup_updates
-        self.warmup_init_lr = warmup_init_lr
-        self.lr_step = (lr - warmup_init_lr) / warmup_updates
-        self.min_lr, self.max_lr = min_lr, lr
-        self.period, self.period_mult, self.lr_shrink = init_period, period_mult, lr_shrink
-        for param_group in self.param_groups:
-            param_group['num_updates'] = 0
+        super().__init__(params, warmup_init_lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)
+        self.cfg = dict(peak_lr=lr, warmup=warmup_updates, init_lr=warmup_init_lr, floor_lr=min_lr, period=init_period,
+                        growth=period_mult, shrink=lr_shrink)
 
     def get_lr_for_step(self, num_updates):
-        if num_updates < self.warmup_updates:
-            return self.warmup_init_lr + num_updates * self.lr_step
-        t = num_updates - self.warmup_updates
-        if self.period_mult == 1:
-            pid = math.floor(t / self.period)
-            t_i = self.period
-            t_curr = t - (self.period * pid)
-        else:
-            pid = math.floor(math.log(1 - t / self.period * (1 - self.period_mult), self.period_mult))
-            t_i = self.period * (self.period_mult ** pid)
-            t_curr = t - (1 - self.period_mult ** pid) / (1 - self.period_mult) * self.period
-        shrink = self.lr_shrink ** pid
-        lo, hi = self.min_lr * shrink, self.max_lr * shrink
-        return lo + 0.5 * (hi - lo) * (1 + math.cos(math.pi * t_curr / t_i))
-
-    def step(self, closure=None):
-        loss = super().step(closure)
-        for param_group in self.param_groups:
-            param_group['num_updates'] += 1
-            param_group['lr'] = self.get_lr_for_step(param_group['num_updates'])
-        return loss
+        return cosine_lr(num_updates, **self.cfg)
 
 
-_METHODS = {"adam": Adam, "adam_inverse_sqrt": AdamInverseSqrtWithWarmup, "adam_cosine": AdamCosineWithWarmup}
-_ARGS = {
-    "adam": {"lr", "eps", "weight_decay"},
-    "adam_inverse_sqrt": {"lr", "eps", "weight_decay", "warmup_updates", "warmup_init_lr", "exp_factor"},
-    "adam_cosine": {"lr", "eps", "weight_decay", "warmup_updates", "warmup_init_lr", "min_lr", "init_period",
-                    "period_mult", "lr_shrink"},
+# ---- the optimizer string DSL of train_x.py's --optimizer flag (optim.py:211-270) -----------------------------
+_NUMBER = re.compile(r"^[+-]?(\d+(\.\d*)?|\.\d+)$")
+_FAMILY = {
+    "adam": (Adam, {"lr", "eps", "weight_decay"}),
+    "adam_inverse_sqrt": (AdamInverseSqrtWithWarmup, {"lr", "eps", "weight_decay", "warmup_updates", "warmup_init_lr",
+                                                      "exp_factor"}),
+    "adam_cosine": (AdamCosineWithWarmup, {"lr", "eps", "weight_decay", "warmup_updates", "warmup_init_lr", "min_lr",
+                                           "init_period", "period_mult", "lr_shrink"}),
 }
+_NOT_BUILT = ("adadelta", "adagrad", "adamax", "asgd", "rmsprop", "rprop", "sgd")  # torch.optim pass-throughs there
+_INTEGER_ARGS = ("warmup_updates", "init_period")
 
 
 def get_optimizer(parameters, s, **extra):
-    """optim.py:211-270: "adam_inverse_sqrt,beta1=0.9,beta2=0.98,lr=0.0001".  Only the Adam family of the
-    published recipes is built for the B200 path; the torch.optim pass-throughs of the reference (sgd, adagrad,
-    ...) raise NotImplementedError instead of silently running a different code path.  `extra` forwards
-    keyword arguments such as clip_grad_norm=5.0."""
-    if "," in s:
-        method = s[:s.find(',')]
-        optim_params = {}
-        for x in s[s.find(',') + 1:].split(','):
-            split = x.split('=')
-            assert len(split) == 2
-            assert re.match(r"^[+-]?(\d+(\.\d*)?|\.\d+)$", split[1]) is not None
-            optim_params[split[0]] = float(split[1])
-    else:
-        method = s
-        optim_params = {}
-    if method not in _METHODS:
-        if method in ("adadelta", "adagrad", "adamax", "asgd", "rmsprop", "rprop", "sgd"):
-            raise NotImplementedError("optimizer %r is outside the B200 path (only the Adam family is fused)" % method)
+    """"adam_inverse_sqrt,beta1=0.9,beta2=0.98,lr=0.0001" -> optimizer, like the reference's parser: a method name
+    followed by comma-separated name=number pairs; beta1 / beta2 fold into `betas`; an argument the class does not
+    take is an error.  Only the Adam family of the published recipes is built for the B200 path — the reference's
+    torch.optim pass-throughs raise NotImplementedError instead of silently running a different code path.
+    `extra` forwards keyword arguments such as clip_grad_norm=5.0."""
+    method, _, tail = s.partition(",")
+    given = {}
+    for item in filter(None, tail.split(",")):
+        name, eq, value = item.partition("=")
+        if not eq or "=" in value or _NUMBER.match(value) is None:
+            raise AssertionError("optimizer argument %r is not of the form name=number" % item)
+        given[name] = float(value)
+    if method in _NOT_BUILT:
+        raise NotImplementedError("optimizer %r is outside the B200 path (only the Adam family is fused)" % method)
+    if method not in _FAMILY:
         raise Exception('Unknown optimization method: "%s"' % method)
-    optim_params['betas'] = (optim_params.pop('beta1', 0.9), optim_params.pop('beta2', 0.999))
-    unexpected = set(optim_params) - _ARGS[method] - {"betas"}
-    if unexpected:
-        raise Exception('Unexpected parameters: expected "%s", got "%s"' % (sorted(_ARGS[method]), sorted(optim_params)))
-    for k in ("warmup_updates", "init_period"):
-        if k in optim_params:
-            optim_params[k] = int(optim_params[k])
-    optim_params.update(extra)
-    return _METHODS[method](parameters, **optim_params)
+    cls, accepted = _FAMILY[method]
+    kwargs = {"betas": (given.pop("beta1", 0.9), given.pop("beta2", 0.999))}
+    unknown = sorted(set(given) - accepted)
+    if unknown:
+        raise Exception('Unexpected parameters: expected "%s", got "%s"' % (sorted(accepted), unknown))
+    kwargs.update({k: (int(v) if k in _INTEGER_ARGS else v) for k, v in given.items()})
+    kwargs.update(extra)
+    return cls(parameters, **kwargs)
 
 
 def tag_parameters(model):
