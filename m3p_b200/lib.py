@@ -136,6 +136,14 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        # a fresh checkout (the .so is git-ignored): build it in-tree if the toolchain is here — still no fallback
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:  # noqa: BLE001 — reported below with the original cause
+            raise M3PError("libm3p_sm100.so is missing and could not be built (%s); build it with "
+                           "`python -m m3p_b200.build` (there is no CPU or PyTorch fallback for the M3P hot path)" % e)
+    if not os.path.exists(LIB_PATH):
         raise M3PError(
             "libm3p_sm100.so not found at %s — build it with `python -m m3p_b200.build` "
             "(there is no CPU or PyTorch fallback for the M3P hot path)" % LIB_PATH)
