@@ -114,3 +114,26 @@ def test_optimizer_oracle_matches_reference_adam(golden_dir):
             O.adam_step(p, gr * coef, mi, vi, s + 1, lr, kw["betas"], kw["eps"], kw["weight_decay"])
             assert _close(p, w, 1e-6)
         lr = O.lr_inverse_sqrt(s + 1, kw["lr"], kw["warmup_updates"], kw["warmup_init_lr"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_rounding_matched_mode_stays_close_to_the_reference(golden_dir, name):
+    """oracle.rounding_matched() (bf16 rounding at the kernels' rounding points, straight-through gradients) is the
+    same algorithm: on the reference's own fixtures it stays within bf16 noise of the fp32 reference outputs and
+    gradients, and leaves padded rows exactly zero."""
+    g, sd = _load(golden_dir, name)
+    cfg, batch = g["config"], g["batch"]
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "pred_layer.proj.weight"}
+    leaf["pred_layer.proj.weight"] = leaf["embeddings.weight"]
+    with O.rounding_matched():
+        enc, losses, total = O.pretrain_step_losses(leaf, cfg["n_layers"], cfg["n_heads"], batch, cfg["sample_n"])
+    total.backward()
+    ref = g["joint"]
+    assert _close(enc.detach(), ref["enc"], 2e-2)
+    for k in ("mlm", "mrm", "mrfr", "rel"):
+        assert abs(float(losses[k]) - float(ref["losses"][k])) < 2e-2 * abs(float(ref["losses"][k])), k
+    assert _close(leaf["ffns.0.lin1.weight"].grad, ref["grads"]["ffns.0.lin1.weight"], 5e-2)
+    S = enc.shape[0]
+    lengths = batch["lengths"] + batch["lengths_img"]
+    pad = torch.arange(S)[:, None] >= lengths[None, :]
+    assert float(enc.detach()[pad].abs().max()) == 0.0 if bool(pad.any()) else True
