@@ -63,11 +63,15 @@ M3P_API int m3p_set_seed_mix(const uint64_t* device_word);
  * Epilogues (v = alpha * acc + bias[n]):
  *   M3P_EPI_LINEAR   out = v                                   (bf16 or fp32; fp32 may accumulate)
  *   M3P_EPI_GELU     out2 = gelu_erf(v), out = gelu_erf'(v) (stash for bwd)   transformer.py:48-56,224
- *   M3P_EPI_DROP_RES out = aux + dropout(v)        (aux = residual)        transformer.py:951-952,956
+ *   M3P_EPI_DROP_RES out = aux + dropout(v)        (aux = residual; bf16 -> bf16 or, with out_f32 and
+ *                    aux_f32, fp32 -> fp32: the residual stream of the encoder)  transformer.py:951-952,956
  *   M3P_EPI_DGELU    out = v * aux                 (aux = the stashed gelu_erf'; backward of :224)
  *   M3P_EPI_TANH     out = tanh(v)                                          transformer.py:556-557
  *   M3P_EPI_DTANH    out = v * (1 - aux^2)         (aux = tanh output; backward of :557)
- * split_k > 1 requires out_f32 = 1 and accumulate = 1 (partial sums are reduced with red.add).
+ * split_k > 1 requires out_f32 = 1 and either accumulate = 1 (partial sums are reduced with red.add: the
+ * fp32 sum depends on arrival order) or split_stride > 0 (K split s stores its partial at out + s * split_stride
+ * elements; m3p_sum_slabs_bf16 adds the slabs in index order — deterministic, used wherever the sum is rounded
+ * to bf16 afterwards).
  * Pitches are in elements; lda, ldb must be multiples of 8 (TMA 16-byte rule).
  * ------------------------------------------------------------------------------------------ */
 enum {
@@ -104,6 +108,11 @@ typedef struct m3p_gemm_args {
    * produces (e.g. d b1 of the FFN from the lin2 dgrad, transformer.py:223), saving a pass over `out`.
    * bf16 outputs on the TMA path only (16-byte aligned bases and pitches); otherwise M3P_ERR_UNSUPPORTED. */
   float* colsum;
+  int64_t split_stride; /* elements between the per-split output slabs (fp32, !accumulate); 0 = none */
+  /* fp32 residual stream: M3P_EPI_DROP_RES with out_f32 = 1 reads an fp32 residual (aux_f32 = 1, ldaux in floats)
+   * and stores the pre-LayerNorm sum in fp32, so the residual stream is never rounded to bf16
+   * (transformer.py:951-952,956 run in fp32 in the reference). */
+  int32_t aux_f32;
 } m3p_gemm_args;
 
 M3P_API int m3p_gemm_bf16(const m3p_gemm_args* args, m3p_stream_t stream);
@@ -141,15 +150,29 @@ M3P_API int m3p_attention_fwd(const m3p_attn_args* args, m3p_stream_t stream);
 M3P_API int m3p_attention_bwd(const m3p_attn_args* args, m3p_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * LayerNorm (eps 1e-12, biased variance, affine) over the last dim of a bf16 [rows][d] tensor.
+ * LayerNorm (eps 1e-12, biased variance, affine) over the last dim of a [rows][d] tensor (bf16, or fp32 with
+ * x_f32 = 1: the encoder's pre-LayerNorm sums are kept in fp32).
  * Replaces layer_norm1 / layer_norm2 + the `tensor *= mask` that follows layer_norm2
  * (transformer.py:953,957-958) and BertPredictionHeadTransform.LayerNorm (:605).
  * Row mask: row = b*S + s is valid iff s < seqlen[b]; invalid rows are written as exact zeros.
- * seqlen = NULL disables the mask.  mean/rstd [rows] are stashed for the backward.
+ * seqlen = NULL disables the mask.  y is the bf16 tensor-core operand copy of the result; y_f32 (optional) the
+ * fp32 copy that the next residual add reads.  mean/rstd [rows] are stashed for the backward.
  * ------------------------------------------------------------------------------------------ */
-M3P_API int m3p_layernorm_fwd(const void* x, const float* gamma, const float* beta, const int32_t* seqlen,
-                              int64_t S, void* y, float* mean, float* rstd, int64_t rows, int64_t d, float eps,
-                              m3p_stream_t stream);
+typedef struct m3p_ln_fwd_args {
+  const void* x;
+  int32_t x_f32;
+  const float* gamma;
+  const float* beta;
+  const int32_t* seqlen;
+  int64_t S;
+  void* y;      /* bf16 [rows][d] */
+  float* y_f32; /* optional fp32 [rows][d] */
+  float* mean;
+  float* rstd;
+  int64_t rows, d;
+  float eps;
+} m3p_ln_fwd_args;
+M3P_API int m3p_layernorm_fwd(const m3p_ln_fwd_args* args, m3p_stream_t stream);
 
 /* Backward of LayerNorm, fused with the pieces that surround it on the path:
  *   dy_eff  = rowmask * dropout_dy(dy)             dropout that FOLLOWED the LN (embeddings :266,943)
@@ -157,7 +180,9 @@ M3P_API int m3p_layernorm_fwd(const void* x, const float* gamma, const float* be
  *   dx_drop = dropout_dx(dx)                       dropout that PRECEDED the residual add (:951, :226)
  *   dgamma += sum dy_eff*xhat ; dbeta += sum dy_eff ; dbias += sum_rows dx_drop (bias of the linear
  *   whose output fed the residual add).  Any of dx_drop / dgamma / dbeta / dbias may be NULL.
- * dtype flags select fp32 (1) or bf16 (0) for x, dy, dx; supported: (0,0,0) (1,0,1) (1,1,0) (1,0,0). */
+ * dtype flags select fp32 (1) or bf16 (0) for x, dy, dx; supported: (0,0,0) (1,0,1) (1,1,0) (1,0,0) (1,1,1).
+ * The encoder layers run (1,1,1): fp32 pre-LN sums, fp32 residual-gradient chain; dx_drop is the bf16 operand
+ * copy of dx (after the dropout mask) that the following dgrad / wgrad GEMMs read. */
 typedef struct m3p_ln_bwd_args {
   const void* dy;
   const void* x;
@@ -190,6 +215,10 @@ M3P_API int m3p_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows,
 
 /* out = bf16(scale * in): refreshes the bf16 tensor-core copies of the fp32 master parameters. */
 M3P_API int m3p_cast_f32_bf16(const float* in, void* out, int64_t n, float scale, m3p_stream_t stream);
+/* out[i] = bf16(sum_{s < n_slabs} in[s * slab_stride + i]), slabs added in index order (deterministic reduction
+ * of the split-K partials written with m3p_gemm_args.split_stride; d rows of the MLM head, transformer.py:104-117). */
+M3P_API int m3p_sum_slabs_bf16(const float* in, int64_t n_slabs, int64_t slab_stride, void* out, int64_t n,
+                               m3p_stream_t stream);
 /* du = dg * gp, bf16, gp = gelu_erf'(u) as stashed by the M3P_EPI_GELU epilogue: backward of the
  * activation of BertPredictionHeadTransform (transformer.py:603-604; the FFN's GELU backward is fused
  * into a GEMM epilogue instead). */
@@ -276,6 +305,7 @@ typedef struct m3p_embed_args {
   float* emb_mean;
   float* emb_rstd;
   void* h0; /* [B*S][d] bf16 */
+  float* h0_f32; /* optional [B*S][d] fp32 copy of h0 before rounding: the residual the first layer adds to */
 } m3p_embed_args;
 M3P_API int m3p_embed_fwd(const m3p_embed_args* args, m3p_stream_t stream);
 

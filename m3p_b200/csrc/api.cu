@@ -92,10 +92,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 static int encode_cached(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
-                         const uint64_t* pitches_elems, const uint32_t* box) {
+                         const uint64_t* pitches_elems, const uint32_t* box, int elem_bytes = 2) {
   TmapKey key{};
   key.v[0] = reinterpret_cast<uint64_t>(ptr);
   key.v[1] = (uint64_t)rank;
+  key.v[9] = (uint64_t)elem_bytes;
   for (int i = 0; i < rank; ++i) {
     key.v[2 + i] = dims[i];
     key.v[5 + i] = (i + 1 < rank) ? pitches_elems[i] : 0;
@@ -113,7 +114,7 @@ static int encode_cached(CUtensorMap* out, const void* ptr, int rank, const uint
   cuuint32_t bdim[3];
   cuuint32_t estr[3] = {1, 1, 1};
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; }
-  for (int i = 0; i + 1 < rank; ++i) gstride[i] = pitches_elems[i] * 2;  // bytes
+  for (int i = 0; i + 1 < rank; ++i) gstride[i] = pitches_elems[i] * (uint64_t)elem_bytes;  // bytes
   for (int i = 0; i + 1 < rank; ++i)
     if (gstride[i] % 16 != 0) {
       set_last_error("TMA: row pitch %llu bytes is not a multiple of 16", (unsigned long long)gstride[i]);
@@ -121,8 +122,8 @@ static int encode_cached(CUtensorMap* out, const void* ptr, int rank, const uint
     }
   // the box's inner extent picks the swizzle: 64 bf16 = 128-byte rows (operand tiles), 32 bf16 = 64-byte rows
   // (the GEMM epilogue's staging tiles)
-  const CUtensorMapSwizzle swz = (box[0] * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim,
+  const CUtensorMapSwizzle swz = (box[0] * elem_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim,
                   gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -144,6 +145,14 @@ int get_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t 
   const uint64_t pitches[1] = {pitch_elems};
   const uint32_t box[2] = {box0, box1};
   return encode_cached(out, ptr, 2, dims, pitches, box);
+}
+
+int get_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t pitch_elems,
+                    uint32_t box0, uint32_t box1) {
+  const uint64_t dims[2] = {dim0, dim1};
+  const uint64_t pitches[1] = {pitch_elems};
+  const uint32_t box[2] = {box0, box1};
+  return encode_cached(out, ptr, 2, dims, pitches, box, 4);
 }
 
 int get_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t dim2,

@@ -34,6 +34,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // 2-D bf16 tensor: dim0 (contiguous) x dim1, row pitch in elements, box0 x box1, 128B swizzle.
 int get_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1,
                      uint64_t pitch_elems, uint32_t box0, uint32_t box1);
+// 2-D fp32 tensor (the GEMM epilogue's fp32 residual tiles: box0 = 16 floats = 64-byte rows, 64B swizzle).
+int get_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t pitch_elems,
+                    uint32_t box0, uint32_t box1);
 // 3-D bf16 tensor: dim0 (contiguous) x dim1 x dim2 with element pitches pitch1, pitch2.
 int get_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1,
                      uint64_t dim2, uint64_t pitch1, uint64_t pitch2, uint32_t box0, uint32_t box1,
@@ -57,7 +60,7 @@ __device__ __forceinline__ void mix_seed(const uint64_t* mix, uint32_t& lo, uint
 // ---- dropout generator -------------------------------------------------------------------------
 // One 32-bit hash per PAIR of consecutive elements; each 16-bit half decides one element:
 // keep iff half >= thr16, thr16 = round(p * 65536).  Element index is the row-major linear index
-// of the tensor the mask applies to, taken modulo 2^32.  tests/emu_ops.py restates this in torch.
+// of the tensor the mask applies to, taken modulo 2^32.  tests/test_dropout_generator.py restates it in numpy.
 __host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t pair_idx, uint32_t seed_lo,
                                                        uint32_t seed_hi) {
   // two multiply / xor-shift rounds (7 integer instructions per element PAIR): plenty for a Bernoulli

@@ -72,12 +72,12 @@ static int ew_grid(long long rows) {
 // =================================================================================================
 // LayerNorm forward:  y = mask * ((x - mean) * rstd * gamma + beta)      transformer.py:953,957-958
 // =================================================================================================
-template <int MAXC>
+template <typename XT, int MAXC>
 __global__ void __launch_bounds__(EW_THREADS)
-ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+ln_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ beta, const int32_t* __restrict__ seqlen, long long S,
-              __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-              long long rows, int d, float eps) {
+              __nv_bfloat16* __restrict__ y, float* __restrict__ y32, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, long long rows, int d, float eps) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * EW_WARPS;
@@ -118,6 +118,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = valid ? fmaf((v[c][j] - mean) * rstd, g[j], b[j]) : 0.f;
         store8(y + row * d + ch * 8, o);
+        if (y32 != nullptr) store8(y32 + row * d + ch * 8, o);  // the fp32 copy the residual add of the next linear reads
       }
     }
     if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
@@ -406,6 +407,24 @@ cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ o
     store8(out + i * 8, v);
   }
 }
+// out = bf16(sum_s in[s * stride + i]), slabs added in index order: the deterministic reduction of split-K partials
+// (m3p_gemm_args.split_stride) — no atomics, so a bf16 result cannot flip with the arrival order of the partial sums
+__global__ void __launch_bounds__(EW_THREADS)
+sum_slabs_bf16_kernel(const float* __restrict__ in, int n_slabs, long long stride, __nv_bfloat16* __restrict__ out,
+                      long long n8) {
+  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * EW_THREADS) {
+    float acc[8];
+    load8(in + i * 8, acc);
+    for (int s = 1; s < n_slabs; ++s) {
+      float v[8];
+      load8(in + (long long)s * stride + i * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+    store8(out + i * 8, acc);
+  }
+}
 // (A, B, F) fp32 -> (B, A, F) bf16     (seq-first reference inputs -> batch-major rows)
 __global__ void __launch_bounds__(EW_THREADS)
 permute_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int A, int B, int F8) {
@@ -649,21 +668,29 @@ scatter_add_rows_f32_kernel(const float* __restrict__ src, const int64_t* __rest
 // =================================================================================================
 using namespace m3p;
 
-extern "C" int m3p_layernorm_fwd(const void* x, const float* gamma, const float* beta, const int32_t* seqlen,
-                                 int64_t S, void* y, float* mean, float* rstd, int64_t rows, int64_t d, float eps,
-                                 m3p_stream_t stream_) {
+template <typename XT>
+static void launch_ln_fwd(const m3p_ln_fwd_args* a, cudaStream_t stream) {
+  const int grid = ew_grid(a->rows);
+  auto X = reinterpret_cast<const XT*>(a->x);
+  auto Y = reinterpret_cast<__nv_bfloat16*>(a->y);
+  const int d = (int)a->d;
+#define M3P_LN_FWD(MAXC) ln_fwd_kernel<XT, MAXC><<<grid, EW_THREADS, 0, stream>>>( \
+      X, a->gamma, a->beta, a->seqlen, a->S, Y, a->y_f32, a->mean, a->rstd, a->rows, d, a->eps)
+  if (d <= 256) M3P_LN_FWD(1);
+  else if (d <= 768) M3P_LN_FWD(3);
+  else if (d <= 1024) M3P_LN_FWD(4);
+  else M3P_LN_FWD(8);
+#undef M3P_LN_FWD
+}
+
+extern "C" int m3p_layernorm_fwd(const m3p_ln_fwd_args* a, m3p_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  M3P_REQUIRE(x && gamma && beta && y && mean && rstd, "m3p_layernorm_fwd: null pointer");
-  M3P_REQUIRE(rows > 0 && d > 0 && d % 8 == 0 && d <= 2048, "m3p_layernorm_fwd: d=%lld must be a multiple of 8, <= 2048",
-              (long long)d);
-  M3P_REQUIRE(seqlen == nullptr || S > 0, "m3p_layernorm_fwd: S must be > 0 with a row mask");
-  const int grid = ew_grid(rows);
-  auto X = reinterpret_cast<const __nv_bfloat16*>(x);
-  auto Y = reinterpret_cast<__nv_bfloat16*>(y);
-  if (d <= 256) ln_fwd_kernel<1><<<grid, EW_THREADS, 0, stream>>>(X, gamma, beta, seqlen, S, Y, mean, rstd, rows, (int)d, eps);
-  else if (d <= 768) ln_fwd_kernel<3><<<grid, EW_THREADS, 0, stream>>>(X, gamma, beta, seqlen, S, Y, mean, rstd, rows, (int)d, eps);
-  else if (d <= 1024) ln_fwd_kernel<4><<<grid, EW_THREADS, 0, stream>>>(X, gamma, beta, seqlen, S, Y, mean, rstd, rows, (int)d, eps);
-  else ln_fwd_kernel<8><<<grid, EW_THREADS, 0, stream>>>(X, gamma, beta, seqlen, S, Y, mean, rstd, rows, (int)d, eps);
+  M3P_REQUIRE(a && a->x && a->gamma && a->beta && a->y && a->mean && a->rstd, "m3p_layernorm_fwd: null pointer");
+  M3P_REQUIRE(a->rows > 0 && a->d > 0 && a->d % 8 == 0 && a->d <= 2048,
+              "m3p_layernorm_fwd: d=%lld must be a multiple of 8, <= 2048", (long long)a->d);
+  M3P_REQUIRE(a->seqlen == nullptr || a->S > 0, "m3p_layernorm_fwd: S must be > 0 with a row mask");
+  if (a->x_f32) launch_ln_fwd<float>(a, stream);
+  else launch_ln_fwd<__nv_bfloat16>(a, stream);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }
@@ -696,6 +723,7 @@ static int layernorm_bwd_impl(const m3p_ln_bwd_args* a, m3p_stream_t stream_, in
     case 5: return launch_ln_bwd<float, __nv_bfloat16, float>(p, stream, phases);
     case 6: return launch_ln_bwd<float, float, __nv_bfloat16>(p, stream, phases);
     case 4: return launch_ln_bwd<float, __nv_bfloat16, __nv_bfloat16>(p, stream, phases);
+    case 7: return launch_ln_bwd<float, float, float>(p, stream, phases);
     default:
       set_last_error("m3p_layernorm_bwd: unsupported dtype combination x_f32=%d dy_f32=%d dx_f32=%d", a->x_f32,
                      a->dy_f32, a->dx_f32);
@@ -734,6 +762,21 @@ extern "C" int m3p_cast_f32_bf16(const float* in, void* out, int64_t n, float sc
   long long g = (n8 + EW_THREADS - 1) / EW_THREADS;
   const long long cap = (long long)sm_count() * 16;
   cast_f32_bf16_kernel<<<(int)(g < cap ? g : cap), EW_THREADS, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n8, scale);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_sum_slabs_bf16(const float* in, int64_t n_slabs, int64_t slab_stride, void* out, int64_t n,
+                                  m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(in && out, "m3p_sum_slabs_bf16: null pointer");
+  M3P_REQUIRE(n > 0 && n % 8 == 0 && n_slabs >= 1 && n_slabs < (1 << 20) && slab_stride % 4 == 0 && slab_stride >= n,
+              "m3p_sum_slabs_bf16: n must be a positive multiple of 8, slab_stride a multiple of 4 and >= n");
+  const long long n8 = n / 8;
+  long long g = (n8 + EW_THREADS - 1) / EW_THREADS;
+  const long long cap = (long long)sm_count() * 16;
+  sum_slabs_bf16_kernel<<<(int)(g < cap ? g : cap), EW_THREADS, 0, stream>>>(in, (int)n_slabs, slab_stride,
+                                                                           reinterpret_cast<__nv_bfloat16*>(out), n8);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }

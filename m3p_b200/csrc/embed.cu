@@ -200,6 +200,7 @@ embed_fwd_kernel(const m3p_embed_args a, const uint32_t thr16, const float scale
           for (int j = 0; j < 8; ++j) y[c][j] = 0.f;
         }
         st8b(h0 + row * d + ch * 8, y[c]);
+        if (a.h0_f32 != nullptr) st8f(a.h0_f32 + row * d + ch * 8, y[c]);
       }
     }
   }

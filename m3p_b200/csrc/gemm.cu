@@ -67,6 +67,7 @@ struct GemmKernelParams {
   int vec_ok;  // all pitches / bases allow 16-byte vector access
   int tma_store;  // bf16 outputs leave through smem staging + cp.async.bulk.tensor stores
   float* colsum;  // optional [N]: += column sums of the stored (bf16-rounded) output
+  long long split_stride;  // fp32 output, split_k > 1, !accumulate: K split ks stores its partial at out + ks * split_stride
 };
 
 // Unit order: K split fastest, then the tile dimension with FEWER tiles.  Units that are adjacent in this order
@@ -131,6 +132,24 @@ __device__ __forceinline__ void unstage_bf16x16(const uint8_t* stg, int r, int c
   unpack_bf16x16(t, x);
 }
 
+// fp32 staging tiles ([32 rows][16 floats] = the same 64-byte rows, same swizzle): 4 chunks of 16 bytes per row
+__device__ __forceinline__ void stage_f32x16(uint8_t* stg, int r, const float* v) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<float4*>(stg + stg_off(r, c)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+__device__ __forceinline__ void unstage_f32x16(const uint8_t* stg, int r, float* x) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 t = *reinterpret_cast<const float4*>(stg + stg_off(r, c));
+    x[4 * c] = t.x; x[4 * c + 1] = t.y; x[4 * c + 2] = t.z; x[4 * c + 3] = t.w;
+  }
+}
+// fp32 residual stream: M3P_EPI_DROP_RES with an fp32 output takes an fp32 aux (residual) as well and runs through
+// the same TMA ring as the bf16 epilogues, 16 columns per staging group instead of 32
+template <int EPI, bool OUT_F32>
+constexpr bool f32_ring() { return OUT_F32 && EPI == M3P_EPI_DROP_RES; }
+
 // v = epilogue(alpha * acc + bias [, x]) for 16 columns of one row; gq = gelu(.) for M3P_EPI_GELU (v = gelu').
 // x: the chunk's aux values (residual / stashed gelu' / tanh output); e0: row-major element index of the chunk's
 // first element (dropout counter).
@@ -185,10 +204,14 @@ __device__ __forceinline__ void epilogue_math(const GemmKernelParams& p, const u
 template <int EPI, bool OUT_F32>
 __device__ __forceinline__ void epilogue_chunk_direct(const GemmKernelParams& p, const uint32_t* acc, const float* sbias,
                                                       long long row, int col0, int ncols, uint32_t seed_lo,
-                                                      uint32_t seed_hi) {
+                                                      uint32_t seed_hi, long long slab_off) {
   float v[EW], gq[EW], x[EW];
   const bool full = (ncols == EW) && p.vec_ok;
-  if constexpr (epi_has_aux<EPI>()) {
+  if constexpr (f32_ring<EPI, OUT_F32>()) {
+    const float* ap = reinterpret_cast<const float*>(p.aux) + row * p.ldaux + col0;
+#pragma unroll
+    for (int j = 0; j < EW; ++j) x[j] = (j < ncols) ? ap[j] : 0.f;
+  } else if constexpr (epi_has_aux<EPI>()) {
     const __nv_bfloat16* ap = p.aux + row * p.ldaux + col0;
     if (full) {
       uint4 t[2];
@@ -213,7 +236,7 @@ __device__ __forceinline__ void epilogue_chunk_direct(const GemmKernelParams& p,
     }
   }
   if constexpr (OUT_F32) {
-    float* op = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+    float* op = reinterpret_cast<float*>(p.out) + slab_off + row * p.ldo + col0;
     if (full) {
       float4* o4 = reinterpret_cast<float4*>(op);
       if (p.accumulate) {
@@ -260,7 +283,8 @@ struct GemmCfg {
   // Staging for the TMA epilogue: per epilogue warp a ring of [32 rows][32 cols] bf16 tiles per output.  Epilogues
   // with an aux operand TMA-LOAD the aux tile into the ring slot two groups ahead, overwrite it in place with the
   // result and TMA-STORE it (ring of 3); the others only store (ring of 2).
-  static constexpr int N_OUT = OUT_F32 ? 0 : (EPI == M3P_EPI_GELU ? 2 : 1);
+  static constexpr bool F32R = f32_ring<EPI, OUT_F32>();
+  static constexpr int N_OUT = OUT_F32 ? (F32R ? 1 : 0) : (EPI == M3P_EPI_GELU ? 2 : 1);
   static constexpr int RING = epi_has_aux<EPI>() ? 3 : 2;
   static constexpr uint32_t WARP_STG = N_OUT * RING * STG_TILE;
   static constexpr uint32_t STG_BYTES = EPI_WARPS * WARP_STG;
@@ -433,14 +457,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int q = warp_idx & 3;   // TMEM lane quarter this warp may access
     const int half = ew >> 2;     // which half of the tile's columns this warp drains
     constexpr int NCH = BN / 2 / EW;  // 16-column chunks per warp per tile
-    constexpr int NG = BN / 2 / GW;   // 32-column staging groups per warp per tile
+    constexpr bool F32R = Cfg::F32R;  // fp32 aux + fp32 output through the ring (16 columns per 64-byte tile row)
+    constexpr int GWC = F32R ? EW : GW;  // columns per staging group
+    constexpr int NG = BN / 2 / GWC;     // staging groups per warp per tile
+    constexpr int CPG = GWC / EW;        // 16-column chunks per staging group
     constexpr bool HAS_AUX = epi_has_aux<EPI>();
     constexpr int RING = Cfg::RING;
     const int cbase = half * (BN / 2);
     float* sbias = bias_smem + ew * (BN / 2);
     uint8_t* ring = stg_smem + ew * Cfg::WARP_STG;  // slot b, output o at ring + (b * N_OUT + o) * STG_TILE
     uint64_t* my_aux_bar = aux_bar + ew * 3;
-    const bool use_tma = (!OUT_F32) && p.tma_store;
+    const bool use_tma = (!OUT_F32 || F32R) && p.tma_store;
     uint32_t seed_lo = p.seed_lo, seed_hi = p.seed_hi;
     if constexpr (EPI == M3P_EPI_DROP_RES) mix_seed(p.seed_mix, seed_lo, seed_hi);
 
@@ -460,7 +487,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     };
     auto issue_aux = [&]() {  // lane 0: request the cursor's group, then advance the cursor
-      const int col0 = ax_col + ax_g * GW;
+      const int col0 = ax_col + ax_g * GWC;
       if (ax_u < p.num_units && col0 < p.N && ax_row0 < p.M) {  // a box entirely outside the tensor is skipped
         mbar_arrive_expect_tx(&my_aux_bar[ax_slot], STG_TILE);
         tma_load_2d(ring + ax_slot * STG_TILE, &tmap_aux, &my_aux_bar[ax_slot], col0, ax_row0);
@@ -513,7 +540,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
         for (int g = 0; g < NG; ++g, ++gg) {
           const int b = gg % RING;
-          const int gcol0 = n0 + cbase + g * GW;
+          const int gcol0 = n0 + cbase + g * GWC;
           const bool valid = gcol0 < p.N && row0 < p.M;
           uint8_t* slot = ring + b * Cfg::N_OUT * STG_TILE;
           if constexpr (HAS_AUX) {
@@ -529,21 +556,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             __syncwarp();
           }
 #pragma unroll
-          for (int ci = 0; ci < GW / EW; ++ci) {
-            const int i = g * (GW / EW) + ci, ii = i & 1;
+          for (int ci = 0; ci < CPG; ++ci) {
+            const int i = g * CPG + ci, ii = i & 1;
             tmem_ld_wait16(acc[ii]);
             if (i + 1 < NCH) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
             float v[EW], gq[EW], x[EW];
-            if constexpr (HAS_AUX) unstage_bf16x16(slot, lane, ci, x);
+            if constexpr (F32R) unstage_f32x16(slot, lane, x);
+            else if constexpr (HAS_AUX) unstage_bf16x16(slot, lane, ci, x);
             const uint32_t e0 = static_cast<uint32_t>(row) * static_cast<uint32_t>(p.N) +
                                 static_cast<uint32_t>(gcol0 + ci * EW);
             epilogue_math<EPI>(p, acc[ii], sbias + i * EW, x, e0, seed_lo, seed_hi, v, gq);
-            stage_bf16x16(slot, lane, ci, v);  // in place over the aux values this thread just consumed
+            if constexpr (F32R) stage_f32x16(slot, lane, v);
+            else stage_bf16x16(slot, lane, ci, v);  // in place over the aux values this thread just consumed
             if constexpr (EPI == M3P_EPI_GELU) stage_bf16x16(slot + STG_TILE, lane, ci, gq);
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (p.colsum != nullptr && valid) {
+          if (!F32R && p.colsum != nullptr && valid) {
             // column sums of the staged [32 rows][32 cols] tile: lane = (row parity, column pair); the two half-warps
             // read rows of opposite parity (64-byte rows: two consecutive rows cover all 32 banks)
             const int cp = lane & 15, par = lane >> 4;
@@ -589,7 +618,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int col0 = n0 + cbase + i * EW;
             if (row_ok && col0 < p.N)
               epilogue_chunk_direct<EPI, OUT_F32>(p, acc[ii], sbias + i * EW, row, col0, min(EW, p.N - col0), seed_lo,
-                                                  seed_hi);
+                                                  seed_hi, static_cast<long long>(ks) * p.split_stride);
           }
         }
       }
@@ -655,8 +684,9 @@ template <int BN, bool CTA2>
 static int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                         const CUtensorMap& tx, const GemmKernelParams& p, int epi, bool out_f32, cudaStream_t s) {
   if (out_f32) {
+    if (epi == M3P_EPI_DROP_RES) return launch_gemm<BN, M3P_EPI_DROP_RES, true, CTA2>(ta, tb, to, to2, tx, p, s);
     if (epi != M3P_EPI_LINEAR) {
-      set_last_error("m3p_gemm_bf16: fp32 output only with M3P_EPI_LINEAR");
+      set_last_error("m3p_gemm_bf16: fp32 output only with M3P_EPI_LINEAR or M3P_EPI_DROP_RES");
       return M3P_ERR_UNSUPPORTED;
     }
     return launch_gemm<BN, M3P_EPI_LINEAR, true, CTA2>(ta, tb, to, to2, tx, p, s);
@@ -706,14 +736,20 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   M3P_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "m3p_gemm_bf16: lda/ldb must be multiples of 8");
   M3P_REQUIRE(aligned16(a->a) && aligned16(a->b), "m3p_gemm_bf16: operands must be 16-byte aligned");
   M3P_REQUIRE(a->split_k >= 1, "m3p_gemm_bf16: split_k must be >= 1");
-  M3P_REQUIRE(a->split_k == 1 || (a->out_f32 && a->accumulate),
-              "m3p_gemm_bf16: split_k > 1 needs fp32 accumulate output");
+  M3P_REQUIRE(a->split_k == 1 || (a->out_f32 && (a->accumulate || a->split_stride > 0)),
+              "m3p_gemm_bf16: split_k > 1 needs an fp32 output that accumulates or per-split slabs (split_stride)");
+  M3P_REQUIRE(a->split_stride == 0 || (a->out_f32 && !a->accumulate && a->split_stride % 4 == 0),
+              "m3p_gemm_bf16: split_stride needs a non-accumulating fp32 output and a multiple of 4");
   M3P_REQUIRE(!a->accumulate || a->out_f32, "m3p_gemm_bf16: accumulate needs fp32 output");
   M3P_REQUIRE(a->split_k == 1 || a->bias == nullptr, "m3p_gemm_bf16: split_k > 1 cannot take a bias");
   if (a->epilogue == M3P_EPI_GELU) M3P_REQUIRE(a->out2 != nullptr, "m3p_gemm_bf16: GELU needs out2");
   if (a->epilogue == M3P_EPI_DROP_RES || a->epilogue == M3P_EPI_DGELU || a->epilogue == M3P_EPI_DTANH)
     M3P_REQUIRE(a->aux != nullptr, "m3p_gemm_bf16: epilogue %d needs aux", a->epilogue);
   M3P_REQUIRE(a->drop_p >= 0.f && a->drop_p < 1.f, "m3p_gemm_bf16: drop_p out of range");
+  const bool f32r = a->out_f32 && a->epilogue == M3P_EPI_DROP_RES;  // fp32 residual stream: fp32 aux -> fp32 out
+  M3P_REQUIRE((a->aux_f32 != 0) == f32r, "m3p_gemm_bf16: aux_f32 goes with (and only with) M3P_EPI_DROP_RES + out_f32");
+  M3P_REQUIRE(!f32r || (!a->accumulate && a->split_k == 1 && a->colsum == nullptr),
+              "m3p_gemm_bf16: the fp32 residual epilogue does not accumulate, split K or sum columns");
 
   const int BN = (a->n > 128) ? 256 : 128;
   const bool cta2 = use_cta_pairs() && a->m > BLOCK_M;
@@ -760,12 +796,13 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   p.seed_mix = seed_mix_ptr();
   p.accumulate = a->accumulate;
   p.colsum = a->colsum;
+  p.split_stride = a->split_stride;
   {
     const int osz = a->out_f32 ? 4 : 2;
     bool ok = aligned16(a->out) && ((a->ldo * osz) % 16 == 0);
     if (a->bias) ok = ok && aligned16(a->bias);
     if (a->out2) ok = ok && aligned16(a->out2) && (a->ldo2 % 8 == 0);
-    if (a->aux) ok = ok && aligned16(a->aux) && (a->ldaux % 8 == 0);
+    if (a->aux) ok = ok && aligned16(a->aux) && (a->ldaux % (f32r ? 4 : 8) == 0);
     p.vec_ok = ok ? 1 : 0;
   }
 
@@ -781,8 +818,13 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
 
   // bf16 outputs (and the aux operand): [32 rows][32 cols] SWIZZLE_64B boxes for the TMA epilogue
   CUtensorMap to = ta, to2 = ta, tx = ta;
-  p.tma_store = (!a->out_f32 && p.vec_ok && use_tma_store()) ? 1 : 0;
-  if (p.tma_store) {
+  p.tma_store = ((!a->out_f32 || f32r) && p.vec_ok && use_tma_store()) ? 1 : 0;
+  if (p.tma_store && f32r) {
+    rc = get_tmap_2d_f32(&to, a->out, (uint64_t)a->n, (uint64_t)a->m, (uint64_t)a->ldo, EW, 32);
+    if (rc) return rc;
+    rc = get_tmap_2d_f32(&tx, a->aux, (uint64_t)a->n, (uint64_t)a->m, (uint64_t)a->ldaux, EW, 32);
+    if (rc) return rc;
+  } else if (p.tma_store) {
     rc = get_tmap_2d_bf16(&to, a->out, (uint64_t)a->n, (uint64_t)a->m, (uint64_t)a->ldo, GW, 32);
     if (rc) return rc;
     if (a->epilogue == M3P_EPI_GELU) {

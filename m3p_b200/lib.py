@@ -31,6 +31,8 @@ class GemmArgs(ctypes.Structure):
         ("aux", c_void_p), ("ldaux", c_int64),
         ("drop_p", c_float), ("seed", c_uint64),
         ("colsum", c_void_p),
+        ("split_stride", c_int64),
+        ("aux_f32", c_int32),
     ]
 
 
@@ -40,6 +42,14 @@ class AttnArgs(ctypes.Structure):
         ("B", c_int64), ("S", c_int64), ("H", c_int64),
         ("scale", c_float), ("drop_p", c_float), ("seed", c_uint64),
         ("ctx", c_void_p), ("lse", c_void_p), ("dctx", c_void_p), ("dqkv", c_void_p),
+    ]
+
+
+class LnFwdArgs(ctypes.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("x_f32", c_int32), ("gamma", c_void_p), ("beta", c_void_p), ("seqlen", c_void_p), ("S", c_int64),
+        ("y", c_void_p), ("y_f32", c_void_p), ("mean", c_void_p), ("rstd", c_void_p), ("rows", c_int64), ("d", c_int64),
+        ("eps", c_float),
     ]
 
 
@@ -67,6 +77,7 @@ class EmbedArgs(ctypes.Structure):
         ("pos_emb", c_void_p), ("langs", c_void_p), ("lang_emb", c_void_p), ("seqlen", c_void_p),
         ("ln_emb_g", c_void_p), ("ln_emb_b", c_void_p),
         ("y_pre", c_void_p), ("emb_mean", c_void_p), ("emb_rstd", c_void_p), ("h0", c_void_p),
+        ("h0_f32", c_void_p),
     ]
 
 
@@ -101,13 +112,13 @@ PROTOTYPES = {
     "m3p_gemm_bf16_debug": [POINTER(GemmArgs)] + [c_int32] * 6 + [c_void_p],
     "m3p_attention_fwd": [POINTER(AttnArgs), c_void_p],
     "m3p_attention_bwd": [POINTER(AttnArgs), c_void_p],
-    "m3p_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
-                          c_int64, c_float, c_void_p],
+    "m3p_layernorm_fwd": [POINTER(LnFwdArgs), c_void_p],
     "m3p_layernorm_bwd": [POINTER(LnBwdArgs), c_void_p],
     "m3p_layernorm_bwd_rows": [POINTER(LnBwdArgs), c_void_p],
     "m3p_layernorm_bwd_cols": [POINTER(LnBwdArgs), c_void_p],
     "m3p_colsum_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p],
     "m3p_cast_f32_bf16": [c_void_p, c_void_p, c_int64, c_float, c_void_p],
+    "m3p_sum_slabs_bf16": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p],
     "m3p_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     "m3p_permute_cast_f32_bf16": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
     "m3p_gather_rows_bf16": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p],

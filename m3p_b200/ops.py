@@ -77,7 +77,7 @@ def split_k_for(m, n, k):
 
 def gemm(a, b, m, n, k, out, *, lda=None, ldb=None, ldo=None, a_mn=False, b_mn=False, epi=L.M3P_EPI_LINEAR,
          out_f32=False, accumulate=False, split_k=1, alpha=1.0, bias=None, out2=None, ldo2=None, aux=None,
-         ldaux=None, drop_p=0.0, seed=0, colsum=None):
+         ldaux=None, drop_p=0.0, seed=0, colsum=None, split_stride=0):
     """C[m][n] = sum_k A(m,k) B(n,k) with a fused epilogue (see m3p_gemm_bf16 in the header)."""
     g = L.GemmArgs()
     g.a, g.b = a.data_ptr(), b.data_ptr()
@@ -99,6 +99,8 @@ def gemm(a, b, m, n, k, out, *, lda=None, ldb=None, ldo=None, a_mn=False, b_mn=F
         g.ldaux = aux.stride(0) if ldaux is None else ldaux
     g.drop_p, g.seed = drop_p, seed
     g.colsum = _p(colsum)
+    g.split_stride = split_stride
+    g.aux_f32 = int(aux is not None and aux.dtype == torch.float32)
     L.check(_lib().m3p_gemm_bf16(_byref(g), _stream()), "m3p_gemm_bf16")
     return out
 
@@ -139,11 +141,15 @@ def attention_bwd(qkv, seqlen, B, S, H, scale, drop_p, seed, ctx, lse, dctx, dqk
     L.check(_lib().m3p_attention_bwd(_byref(a), _stream()), "m3p_attention_bwd")
 
 
-def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps, seqlen=None, S=0):
-    rows, d = x.shape
-    L.check(_lib().m3p_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(seqlen), S, y.data_ptr(),
-                                     mean.data_ptr(), rstd.data_ptr(), rows, d, eps, _stream()),
-            "m3p_layernorm_fwd")
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps, seqlen=None, S=0, y32=None):
+    """y (bf16) [, y32 (fp32)] = rowmask * LayerNorm(x); x is bf16 or fp32."""
+    a = L.LnFwdArgs()
+    a.x, a.x_f32 = x.data_ptr(), int(x.dtype == torch.float32)
+    a.gamma, a.beta, a.seqlen, a.S = gamma.data_ptr(), beta.data_ptr(), _p(seqlen), S
+    a.y, a.y_f32, a.mean, a.rstd = y.data_ptr(), _p(y32), mean.data_ptr(), rstd.data_ptr()
+    a.rows, a.d = x.shape
+    a.eps = eps
+    L.check(_lib().m3p_layernorm_fwd(_byref(a), _stream()), "m3p_layernorm_fwd")
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, *, seqlen=None, S=0, dx_drop=None, dx_drop_p=0.0, dx_seed=0,
@@ -175,6 +181,12 @@ def colsum(x, out, rows=None, n=None, ld=None):
 def cast_f32_bf16(src, dst, n=None, scale=1.0):
     n = src.numel() if n is None else n
     L.check(_lib().m3p_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), n, scale, _stream()), "m3p_cast_f32_bf16")
+
+
+def sum_slabs_bf16(src, n_slabs, slab_stride, dst, n):
+    """dst = bf16(sum of the n_slabs fp32 slabs of src, in index order): deterministic split-K reduction."""
+    L.check(_lib().m3p_sum_slabs_bf16(src.data_ptr(), n_slabs, slab_stride, dst.data_ptr(), n, _stream()),
+            "m3p_sum_slabs_bf16")
 
 
 def gelu_bwd(dg, gp, du):

@@ -416,7 +416,8 @@ class TransformerModel(nn.Module):
         lets several forwards be in flight before their backwards (e.g. the CLCM second pass) — the
         backward re-registers the word its forward used.  Returns (host seed, device word tensor)."""
         if self._seed_words is None or self._seed_words.device != self._flat.device:
-            self._seed_words = torch.zeros(self._SEED_SLOTS, dtype=torch.int64, device=self._flat.device)
+            # distinct start values: slot j after k bumps holds j * C + k * INC, so no two calls ever share a word
+            self._seed_words = torch.arange(self._SEED_SLOTS, dtype=torch.int64, device=self._flat.device) * 0x2545F4914F6CDD1D
         slot = self._step % self._SEED_SLOTS
         self._step += 1
         word = self._seed_words[slot:slot + 1]
@@ -626,12 +627,15 @@ class TransformerModel(nn.Module):
         a.seqlen = seqlen.data_ptr()
         a.ln_emb_g = self._w32("layer_norm_emb.weight").data_ptr()
         a.ln_emb_b = self._w32("layer_norm_emb.bias").data_ptr()
-        h = e(M, d)
+        # residual stream: every LayerNorm output exists twice — the bf16 copy the tensor cores read (h) and the
+        # fp32 copy the next residual add reads (h32); the pre-LayerNorm sums x1 / x2 are fp32 only.  Nothing on the
+        # residual path is ever rounded to bf16 (the reference adds in fp32, transformer.py:951-952,956).
+        h, h32 = e(M, d), e(M, d, dt=_F32)
         if spec["flags"] & L.M3P_EMB_LN:
             y_pre, emb_mean, emb_rstd = e(M, d, dt=_F32), e(M, dt=_F32), e(M, dt=_F32)
             a.y_pre, a.emb_mean, a.emb_rstd = y_pre.data_ptr(), emb_mean.data_ptr(), emb_rstd.data_ptr()
             st.update(y_pre=y_pre, emb_mean=emb_mean, emb_rstd=emb_rstd)
-        a.h0 = h.data_ptr()
+        a.h0, a.h0_f32 = h.data_ptr(), h32.data_ptr()
         ops.embed_fwd(a)
         del keep
 
@@ -644,25 +648,29 @@ class TransformerModel(nn.Module):
             ops.linear(h, w["wqkv"], w["bqkv"], qkv)
             ctx, lse = e(M, d), e(B * H * S, dt=_F32)
             ops.attention_fwd(qkv, seqlen, B, S, H, scale, p_att, sa, ctx, lse)
-            x1 = e(M, d)
-            ops.linear(ctx, w["wo"], w["bo"], x1, epi=L.M3P_EPI_DROP_RES, aux=h, drop_p=p_drop, seed=s1)
-            h1, mean1, rstd1 = e(M, d), e(M, dt=_F32), e(M, dt=_F32)
-            ops.layernorm_fwd(x1, w["g1"], w["b1"], h1, mean1, rstd1, LN_EPS)
+            x1 = e(M, d, dt=_F32)
+            ops.linear(ctx, w["wo"], w["bo"], x1, epi=L.M3P_EPI_DROP_RES, aux=h32, drop_p=p_drop, seed=s1, out_f32=True)
+            h1, h1_32, mean1, rstd1 = e(M, d), e(M, d, dt=_F32), e(M, dt=_F32), e(M, dt=_F32)
+            ops.layernorm_fwd(x1, w["g1"], w["b1"], h1, mean1, rstd1, LN_EPS, y32=h1_32)
             gp, g = e(M, 4 * d), e(M, 4 * d)  # gelu'(u) (stash for the backward) and gelu(u)
             ops.linear(h1, w["w1"], w["bb1"], gp, epi=L.M3P_EPI_GELU, out2=g)
-            x2 = e(M, d)
-            ops.linear(g, w["w2"], w["bb2"], x2, epi=L.M3P_EPI_DROP_RES, aux=h1, drop_p=p_drop, seed=s2)
+            x2 = e(M, d, dt=_F32)
+            ops.linear(g, w["w2"], w["bb2"], x2, epi=L.M3P_EPI_DROP_RES, aux=h1_32, drop_p=p_drop, seed=s2, out_f32=True)
             hn, mean2, rstd2 = e(M, d), e(M, dt=_F32), e(M, dt=_F32)
-            ops.layernorm_fwd(x2, w["g2"], w["b2"], hn, mean2, rstd2, LN_EPS, seqlen=seqlen, S=S)
+            hn32 = e(M, d, dt=_F32) if i + 1 < self.n_layers else None  # the last layer's output has no residual reader
+            ops.layernorm_fwd(x2, w["g2"], w["b2"], hn, mean2, rstd2, LN_EPS, seqlen=seqlen, S=S, y32=hn32)
             if need_grad:
                 st["layers"].append(dict(h=h, qkv=qkv, ctx=ctx, lse=lse, x1=x1, h1=h1, mean1=mean1, rstd1=rstd1, gp=gp,
                                          g=g, x2=x2, mean2=mean2, rstd2=rstd2, s1=s1, s2=s2, sa=sa))
-            h = hn
+            h, h32 = hn, hn32
+            del h1_32
         return h, st
 
     def _encode_backward(self, st, dh, want_dximg, want_dtext):
         """Backward of `_encode`: dh [B*S, d] bf16 -> parameter gradients (accumulated into the flat
-        buffer) and, on request, d x_img (R,B,2048) / d text_embed (B,T,d) for FreeLB."""
+        buffer) and, on request, d x_img (R,B,2048) / d text_embed (B,T,d) for FreeLB.  The residual-gradient chain
+        (dh -> dx2 -> dh1 -> dx1 -> dh of the layer below) is fp32 end to end, like autograd's in the reference; the
+        branch gradients that feed tensor-core GEMMs (dx*d, du, dctx, dqkv) are bf16 operand copies."""
         ops.use_current_stream()
         L.load().m3p_set_seed_mix(st["seed_word"].data_ptr())  # the masks this forward drew
         self.attach_grads()
@@ -682,12 +690,11 @@ class TransformerModel(nn.Module):
         for i in reversed(range(self.n_layers)):
             w, gr, s = self._layer_views(i), self._layer_grads(i), st["layers"][i]
             # layer_norm2 (+ row mask) and the FFN dropout           (:956-958, :226)
-            dx2 = e(M, d)
-            dx2d = e(M, d) if p_drop > 0 else None
+            dx2, dx2d = e(M, d, dt=_F32), e(M, d)
             ln2 = dict(seqlen=seqlen, S=S, dx_drop=dx2d, dx_drop_p=p_drop, dx_seed=s["s2"], dgamma=gr["g2"],
                        dbeta=gr["b2"], dbias=gr["bb2"])
             ops.layernorm_bwd(dh, s["x2"], s["mean2"], s["rstd2"], w["g2"], dx2, phase="rows", **ln2)
-            dx2d_ = dx2 if dx2d is None else dx2d
+            dx2d_ = dx2d
             sq.fork()
             sq.run(lambda: ops.layernorm_bwd(dh, s["x2"], s["mean2"], s["rstd2"], w["g2"], dx2, phase="cols", **ln2))
             sq.run(lambda: ops.wgrad(dx2d_, s["g"], gr["w2"]))                  # lin2 wgrad            (:225)
@@ -697,14 +704,13 @@ class TransformerModel(nn.Module):
             sq.fork()
             sq.run(lambda: ops.wgrad(du, s["h1"], gr["w1"]))                    # lin1 wgrad            (:223)
             # lin1 dgrad + residual branch                                     (:223, :956)
-            dh1 = e(M, d)
-            ops.dgrad(du, w["w1"], dh1, epi=L.M3P_EPI_DROP_RES, aux=dx2)
+            dh1 = e(M, d, dt=_F32)
+            ops.dgrad(du, w["w1"], dh1, epi=L.M3P_EPI_DROP_RES, aux=dx2, out_f32=True)
             # layer_norm1 and the attention-output dropout              (:951-953)
-            dx1 = e(M, d)
-            dx1d = e(M, d) if p_drop > 0 else None
+            dx1, dx1d = e(M, d, dt=_F32), e(M, d)
             ln1 = dict(dx_drop=dx1d, dx_drop_p=p_drop, dx_seed=s["s1"], dgamma=gr["g1"], dbeta=gr["b1"], dbias=gr["bo"])
             ops.layernorm_bwd(dh1, s["x1"], s["mean1"], s["rstd1"], w["g1"], dx1, phase="rows", **ln1)
-            dx1d_ = dx1 if dx1d is None else dx1d
+            dx1d_ = dx1d
             sq.fork()
             sq.run(lambda: ops.layernorm_bwd(dh1, s["x1"], s["mean1"], s["rstd1"], w["g1"], dx1, phase="cols", **ln1))
             sq.run(lambda: ops.wgrad(dx1d_, s["ctx"], gr["wo"]))
@@ -716,8 +722,8 @@ class TransformerModel(nn.Module):
             sq.fork()
             sq.run(lambda: ops.colsum(dqkv, gr["bqkv"]))
             sq.run(lambda: ops.wgrad(dqkv, s["h"], gr["wqkv"]))                 # q/k/v projections     (:178-181)
-            dhp = e(M, d)
-            ops.dgrad(dqkv, w["wqkv"], dhp, epi=L.M3P_EPI_DROP_RES, aux=dx1)
+            dhp = e(M, d, dt=_F32)
+            ops.dgrad(dqkv, w["wqkv"], dhp, epi=L.M3P_EPI_DROP_RES, aux=dx1, out_f32=True)
             # the side stream may still be reading these: keep them alive until the join one layer later
             sq.close("layer%d" % i, self._segments["layer%d" % i], (dh, s, dx2, dx2d, du, dh1, dx1, dx1d, dqkv))
             dh = dhp
@@ -1066,14 +1072,18 @@ class _MlmFn(torch.autograd.Function):
         dt = None
         if ctx.needs_input_grad[0]:
             # d rows = dlogits E: a [n x d] output (12 tiles of 256 x 256 for n = 1024) with K = V = 250 002 — without a
-            # K split 12 clusters would each run ~3 900 k-blocks while 62 idle; split K over the whole machine into an
-            # fp32 accumulator, then round once
-            drows32 = torch.zeros(n, d, dtype=_F32, device=dev)
+            # K split 12 clusters would each run ~3 900 k-blocks while 62 idle.  Every K split stores its fp32 partial
+            # in its own slab and one kernel adds the slabs in index order and rounds once: no atomics, so the bf16
+            # gradient entering the encoder backward cannot flip with the arrival order of the partial sums.
             tiles = ((n + 255) // 256) * ((d + 255) // 256)
-            ops.gemm(dlog, model._emb16, n, d, V, drows32, b_mn=True, out_f32=True, accumulate=True,
-                     split_k=max(1, min(32, 148 // max(tiles, 1))))
+            kblocks = (V + 63) // 64
+            split = max(1, min(32, 148 // max(tiles, 1), kblocks))
+            split = -(-kblocks // -(-kblocks // split))  # the library drops empty splits: ceil(kb / ceil(kb / split))
+            slabs = torch.empty(split, n, d, dtype=_F32, device=dev)
+            ops.gemm(dlog, model._emb16, n, d, V, slabs, b_mn=True, out_f32=True, split_k=split, ldo=d,
+                     split_stride=n * d if split > 1 else 0)
             drows = torch.empty(n, d, dtype=_BF16, device=dev)
-            ops.cast_f32_bf16(drows32, drows, n * d)
+            ops.sum_slabs_bf16(slabs, split, n * d, drows, n * d)
             dt = torch.zeros(slen, bs, d, dtype=_BF16, device=dev)
             ops.scatter_rows(drows, idx, bs, bs * d, d, dt, n, d)
         return dt, None, None, None, None, None

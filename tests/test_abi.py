@@ -54,8 +54,8 @@ def test_struct_sizes_match_the_header(lib):
 #include <stdio.h>
 #include "m3p_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(m3p_gemm_args), sizeof(m3p_attn_args), sizeof(m3p_ln_bwd_args),
-         sizeof(m3p_embed_args), sizeof(m3p_embed_bwd_args), sizeof(m3p_adam_args));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(m3p_gemm_args), sizeof(m3p_attn_args), sizeof(m3p_ln_bwd_args),
+         sizeof(m3p_embed_args), sizeof(m3p_embed_bwd_args), sizeof(m3p_adam_args), sizeof(m3p_ln_fwd_args));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as td:
@@ -64,7 +64,7 @@ int main(void) {
         exe = os.path.join(td, "p")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    got = [ctypes.sizeof(t) for t in (L.GemmArgs, L.AttnArgs, L.LnBwdArgs, L.EmbedArgs, L.EmbedBwdArgs, L.AdamArgs)]
+    got = [ctypes.sizeof(t) for t in (L.GemmArgs, L.AttnArgs, L.LnBwdArgs, L.EmbedArgs, L.EmbedBwdArgs, L.AdamArgs, L.LnFwdArgs)]
     assert got == sizes
 
 
