@@ -248,6 +248,16 @@ M3P_API int m3p_cross_entropy_bwd(const void* logits, int64_t ld, const int64_t*
                                   int64_t ignore_index, const float* lse, const float* inv_count,
                                   const float* grad_scale, void* dlogits, int64_t ldd, m3p_stream_t stream);
 
+/* Masked MSE of the MRFR objective (xtrainer.py:2333-2348): *loss = sum_rows weight[row] * sum_f (pred - target)^2
+ * with weight[row] = selected[row] / (n_selected * d) (== F.mse_loss(pred[sel], target[sel]); prepared with the batch,
+ * so nothing syncs).  pred bf16 [n][ld], target fp32 [n][d].  Backward: dpred = 2 * weight * g * (pred - target),
+ * g = *grad_scale (device scalar) or 1; unselected rows are written as zeros. */
+M3P_API int m3p_masked_mse_fwd(const void* pred, int64_t ld, const float* target, const float* weight, int64_t n,
+                               int64_t d, float* loss, m3p_stream_t stream);
+M3P_API int m3p_masked_mse_bwd(const void* pred, int64_t ld, const float* target, const float* weight,
+                               const float* grad_scale, void* dpred, int64_t ldd, int64_t n, int64_t d,
+                               m3p_stream_t stream);
+
 /* seq_relationship / seq_relationship2: Linear(d, 1) (transformer.py:713,716,1196,1200) and backward.
  * tanh_grad != 0: x is the BertPooler tanh output (:556-557) and dx is returned w.r.t. the
  * pre-activation, dx = dout * w * (1 - x^2). */
@@ -256,6 +266,10 @@ M3P_API int m3p_rowdot_fwd(const void* x, const float* w, const float* bias, flo
 M3P_API int m3p_rowdot_bwd(const float* dout, const void* x, const float* w, void* dx, float* dw, float* db,
                            int64_t rows, int64_t d, int32_t tanh_grad, m3p_stream_t stream);
 
+/* dst[i][:] = table[idx[i]][:] (fp32): the nn.Embedding lookup on its own (model.embeddings(ids), used by FreeLB's
+ * embeds_init, xtrainer.py:2700-2705); m3p_scatter_add_rows_f32 with skip_index = padding_idx is its backward. */
+M3P_API int m3p_gather_rows_f32(const float* table, const int64_t* idx, float* dst, int64_t n, int64_t d,
+                                m3p_stream_t stream);
 /* dst[idx[i]][:] += src[i][:] (fp32, atomic), rows with idx == skip_index skipped. */
 M3P_API int m3p_scatter_add_rows_f32(const float* src, const int64_t* idx, int64_t skip_index, float* dst, int64_t n,
                                      int64_t d, m3p_stream_t stream);

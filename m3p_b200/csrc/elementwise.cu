@@ -610,6 +610,72 @@ ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, const int6
 }
 
 // =================================================================================================
+// masked MSE of the MRFR objective (xtrainer.py:2333-2348): F.mse_loss(pred[sel], target[sel]) over the masked
+// regions, written as sum_rows w[row] * sum_f (pred - target)^2 with w[row] = sel[row] / (n_sel * d) prepared with
+// the batch — no boolean gather, no host sync.  Rows with w == 0 are never read.
+// =================================================================================================
+__global__ void __launch_bounds__(EW_THREADS)
+mse_rows_kernel(const __nv_bfloat16* __restrict__ pred, long long ld, const float* __restrict__ target,
+                const float* __restrict__ w, float* __restrict__ row_loss, long long n, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * EW_WARPS;
+  for (long long row = warp0; row < n; row += nwarps) {
+    const float wr = w[row];
+    float acc = 0.f;
+    if (wr != 0.f) {
+      for (int c = lane; c < (d >> 3); c += 32) {
+        float a[8], b[8];
+        load8(pred + row * ld + c * 8, a);
+        load8(target + row * (long long)d + c * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float t = a[j] - b[j]; acc = fmaf(t, t, acc); }
+      }
+      acc = warp_sum(acc) * wr;
+    }
+    if (lane == 0) row_loss[row] = acc;
+  }
+}
+// *out = sum_i x[i], one CTA, fixed order (deterministic)
+__global__ void sum_rows_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float s_sum[32];
+  float sum = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) sum += x[i];
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) t += s_sum[wi];
+    *out = t;
+  }
+}
+// dpred[row][:] = bf16(2 * w[row] * g * (pred - target)); rows with w == 0 get zeros
+__global__ void __launch_bounds__(EW_THREADS)
+mse_bwd_kernel(const __nv_bfloat16* __restrict__ pred, long long ld, const float* __restrict__ target,
+               const float* __restrict__ w, const float* __restrict__ grad_scale, __nv_bfloat16* __restrict__ dpred,
+               long long ldd, long long n, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * EW_WARPS;
+  const float g = grad_scale != nullptr ? *grad_scale : 1.0f;
+  for (long long row = warp0; row < n; row += nwarps) {
+    const float wr = 2.0f * w[row] * g;
+    for (int c = lane; c < (d >> 3); c += 32) {
+      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (wr != 0.f) {
+        float b[8];
+        load8(pred + row * ld + c * 8, a);
+        load8(target + row * (long long)d + c * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = wr * (a[j] - b[j]);
+      }
+      store8(dpred + row * ldd + c * 8, a);
+    }
+  }
+}
+
+// =================================================================================================
 // tiny linear d -> 1 (seq_relationship, transformer.py:713,1196) and its backward
 // =================================================================================================
 __global__ void __launch_bounds__(EW_THREADS)
@@ -642,6 +708,20 @@ rowdot_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restric
   }
   atomicAdd(dw + j, acc);
   if (j == 0) atomicAdd(db, accb);
+}
+
+// dst[i][:] = table[idx[i]][:] (fp32): nn.Embedding lookup kept in fp32 (FreeLB's embeds_init, xtrainer.py:2700-2705)
+__global__ void __launch_bounds__(EW_THREADS)
+gather_rows_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, float* __restrict__ dst,
+                       long long n, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * EW_WARPS;
+  for (long long i = warp0; i < n; i += nwarps) {
+    const float* s = table + idx[i] * d;
+    for (int c = lane; c < (d >> 2); c += 32)
+      *reinterpret_cast<float4*>(dst + i * d + c * 4) = *reinterpret_cast<const float4*>(s + c * 4);
+  }
 }
 
 // bf16 -> fp32 elementwise add into (embedding-style) fp32 rows:  dst[idx[i]][:] += src[i][:]
@@ -864,6 +944,33 @@ extern "C" int m3p_cross_entropy_bwd(const void* logits, int64_t ld, const int64
   return M3P_OK;
 }
 
+extern "C" int m3p_masked_mse_fwd(const void* pred, int64_t ld, const float* target, const float* weight, int64_t n,
+                                  int64_t d, float* loss, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(pred && target && weight && loss, "m3p_masked_mse_fwd: null pointer");
+  M3P_REQUIRE(n > 0 && d > 0 && d % 8 == 0 && ld % 8 == 0 && ld >= d, "m3p_masked_mse_fwd: d and ld must be multiples of 8");
+  float* row_loss = scratch_f32((size_t)n);
+  if (row_loss == nullptr) return M3P_ERR_CUDA;
+  mse_rows_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(pred), ld, target, weight,
+                                                         row_loss, n, (int)d);
+  sum_rows_kernel<<<1, 1024, 0, stream>>>(row_loss, n, loss);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_masked_mse_bwd(const void* pred, int64_t ld, const float* target, const float* weight,
+                                  const float* grad_scale, void* dpred, int64_t ldd, int64_t n, int64_t d,
+                                  m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(pred && target && weight && dpred, "m3p_masked_mse_bwd: null pointer");
+  M3P_REQUIRE(n > 0 && d > 0 && d % 8 == 0 && ld % 8 == 0 && ldd % 8 == 0 && ld >= d && ldd >= d,
+              "m3p_masked_mse_bwd: d and pitches must be multiples of 8");
+  mse_bwd_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(pred), ld, target, weight,
+                                                        grad_scale, reinterpret_cast<__nv_bfloat16*>(dpred), ldd, n, (int)d);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
 extern "C" int m3p_rowdot_fwd(const void* x, const float* w, const float* bias, float* out, int64_t rows, int64_t d,
                               m3p_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -881,6 +988,15 @@ extern "C" int m3p_rowdot_bwd(const float* dout, const void* x, const float* w, 
   rowdot_bwd_kernel<<<(unsigned)((d + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, stream>>>(
       dout, reinterpret_cast<const __nv_bfloat16*>(x), w, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, rows, (int)d,
       (int)tanh_grad);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_gather_rows_f32(const float* table, const int64_t* idx, float* dst, int64_t n, int64_t d,
+                                   m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(table && idx && dst && n > 0 && d > 0 && d % 4 == 0, "m3p_gather_rows_f32: bad arguments");
+  gather_rows_f32_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(table, idx, dst, n, (int)d);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }

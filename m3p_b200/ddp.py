@@ -30,6 +30,16 @@ class GradReducer:
         model._grad_ready_hook = self._segment_ready if self.world > 1 else None
         model._defer_token_grads = self.world > 1 and overlap
         self._dense_sent = False
+        self._accumulating = False
+
+    def accumulate(self):
+        """`with reducer.accumulate():` around every backward of a step EXCEPT the last one (gradient accumulation,
+        `--accumulate_gradients`, xtrainer.py:229-243; the three ascent steps of FreeLB): nothing is sent from inside
+        those backwards — a slice reduced during micro-step 1 would be averaged once and then receive un-averaged
+        local gradients from micro-step 2 while possibly still in flight on NCCL's stream.  The last backward (outside
+        the context) announces the slices as usual; they then hold the accumulated sum.  (Apex DDP with
+        delay_allreduce does the same: one all-reduce when the last backward ends.)"""
+        return _NoSync(self)
 
     def _allreduce(self, buf):
         if self._avg:
@@ -40,7 +50,7 @@ class GradReducer:
 
     # segments are (lo, hi) element ranges of model._flat_grad
     def _segment_ready(self, name, lo, hi):
-        if self.world == 1 or (lo, hi) in self._done:
+        if self.world == 1 or self._accumulating or (lo, hi) in self._done:
             return
         self._done.add((lo, hi))
         buf = self.model._flat_grad[lo:hi]
@@ -76,8 +86,19 @@ class GradReducer:
         dist.all_gather_into_tensor(all_ids, ids, group=self.group)
         dist.all_gather_into_tensor(all_rows, rows, group=self.group)
         g.index_fill_(0, ids, 0.0)
-        g.index_add_(0, all_ids, all_rows)
+        self._scatter_add(m, all_rows, all_ids, g)
         m._emb_touched = [all_ids]  # what the next zero_grad has to clear
+
+    @staticmethod
+    def _scatter_add(m, rows, ids, g):
+        """g[ids[i]] += rows[i]: m3p_scatter_add_rows_f32 on the GPU (one launch, float4 reductions), index_add_ on
+        the CPU test double."""
+        if g.is_cuda:
+            from . import ops
+            ops.use_current_stream()
+            ops.scatter_add_rows_f32(rows, ids, -1, g, ids.numel(), g.shape[1])
+        else:
+            g.index_add_(0, ids, rows)
 
     def _exchange_deferred_rows(self, m, deferred):
         """Tied MLM head under data parallelism: the dense part of d E is already in flight; the embedding
@@ -99,7 +120,7 @@ class GradReducer:
         for buf in self._post:
             buf.div_(self.world)
         self._works, self._post = [], []
-        g.index_add_(0, all_ids, all_rows)
+        self._scatter_add(m, all_rows, all_ids, g)
 
     def finish(self):
         """Call after backward(): reduces whatever has not been sent yet and joins the NCCL stream."""
@@ -147,6 +168,22 @@ class GradReducer:
         self._done = set()
         self._post = []
         self._dense_sent = False
+
+
+class _NoSync:
+    def __init__(self, reducer):
+        self.r = reducer
+
+    def __enter__(self):
+        r = self.r
+        if r._works or r._done:
+            raise RuntimeError("GradReducer.accumulate(): a previous backward already sent gradients; wrap every backward "
+                               "but the last one, and call finish() after the last")
+        self.prev = (r._accumulating, r.model._defer_token_grads)
+        r._accumulating, r.model._defer_token_grads = True, False
+
+    def __exit__(self, *exc):
+        self.r._accumulating, self.r.model._defer_token_grads = self.prev
 
 
 def init_distributed():

@@ -127,9 +127,12 @@ PROTOTYPES = {
                               c_void_p],
     "m3p_cross_entropy_bwd": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int64, c_void_p],
+    "m3p_masked_mse_fwd": [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p],
+    "m3p_masked_mse_bwd": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
     "m3p_rowdot_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
     "m3p_rowdot_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                        c_void_p],
+    "m3p_gather_rows_f32": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
     "m3p_scatter_add_rows_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p],
     "m3p_embed_fwd": [POINTER(EmbedArgs), c_void_p],
     "m3p_embed_bwd_route": [POINTER(EmbedBwdArgs), c_void_p],

@@ -222,6 +222,21 @@ def cross_entropy_bwd(logits, y, V, ignore_index, lse, inv_count, grad_scale, dl
                                          dlogits.data_ptr(), dlogits.stride(0), _stream()), "m3p_cross_entropy_bwd")
 
 
+def masked_mse_fwd(pred, target, weight, loss):
+    global LAUNCHES
+    LAUNCHES += 1
+    n, d = pred.shape
+    L.check(_lib().m3p_masked_mse_fwd(pred.data_ptr(), pred.stride(0), target.data_ptr(), weight.data_ptr(), n, d,
+                                      loss.data_ptr(), _stream()), "m3p_masked_mse_fwd")
+
+
+def masked_mse_bwd(pred, target, weight, grad_scale, dpred):
+    n, d = pred.shape
+    L.check(_lib().m3p_masked_mse_bwd(pred.data_ptr(), pred.stride(0), target.data_ptr(), weight.data_ptr(),
+                                      _p(grad_scale), dpred.data_ptr(), dpred.stride(0), n, d, _stream()),
+            "m3p_masked_mse_bwd")
+
+
 def rowdot_fwd(x, w, bias, out):
     L.check(_lib().m3p_rowdot_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1],
                                   _stream()), "m3p_rowdot_fwd")
@@ -230,6 +245,11 @@ def rowdot_fwd(x, w, bias, out):
 def rowdot_bwd(dout, x, w, dx, dw, db, tanh_grad=False):
     L.check(_lib().m3p_rowdot_bwd(dout.data_ptr(), x.data_ptr(), w.data_ptr(), dx.data_ptr(), dw.data_ptr(),
                                   db.data_ptr(), x.shape[0], x.shape[1], int(tanh_grad), _stream()), "m3p_rowdot_bwd")
+
+
+def gather_rows_f32(table, idx, dst, n, d):
+    L.check(_lib().m3p_gather_rows_f32(table.data_ptr(), idx.data_ptr(), dst.data_ptr(), n, d, _stream()),
+            "m3p_gather_rows_f32")
 
 
 def scatter_add_rows_f32(src, idx, skip_index, dst, n, d):

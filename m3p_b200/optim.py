@@ -144,10 +144,24 @@ class Adam(torch.optim.Optimizer):
         return {"param_groups": groups, "n_steps": self.n_steps,
                 "moments": [(m.clone(), v.clone()) for m, v in self._moments.values()]}
 
-    def load_state_dict(self, sd):
+    def load_state_dict(self, sd, restore_moments=False):
+        """The reference's checkpoint reload keeps only `num_updates` and `lr` of each param group and starts Adam's
+        moments AND its bias-correction step from zero (xtrainer.py:579-590, "Not reloading checkpoint optimizer"):
+        that is the default here — moments dropped, n_steps = 0, so the bias correction matches the zeroed moments.
+        restore_moments=True resumes exactly instead (moments and step count of this optimizer's own state_dict)."""
         for g, saved in zip(self.param_groups, sd["param_groups"]):
             g.update({k: v for k, v in saved.items() if k != "params"})
-        self.n_steps = int(sd.get("n_steps", 0))
+        if restore_moments and sd.get("moments") is not None:
+            work = self._work_list()
+            if len(work) != len(sd["moments"]):
+                raise ValueError("optimizer state has %d moment buffers, this optimizer %d (run one backward first so "
+                                 "the flat gradient buffers exist)" % (len(sd["moments"]), len(work)))
+            for (_, p, _, _, _), (m, v) in zip(work, sd["moments"]):
+                self._moments[p.data_ptr()] = (m.to(p.device).clone(), v.to(p.device).clone())
+            self.n_steps = int(sd.get("n_steps", 0))
+        else:
+            self._moments = {}
+            self.n_steps = 0
 
 
 # ---- learning-rate schedules: pure functions of the update count (the classes below only hold their settings) ----

@@ -29,6 +29,39 @@ def prepare_batch(batch):
     return b
 
 
+class _MaskedMse(torch.autograd.Function):
+    """F.mse_loss(pred[sel], target[sel]) of the MRFR objective (xtrainer.py:2333-2348) as two kernels
+    (m3p_masked_mse_fwd / _bwd): pred (n, d) bf16, target (n, d) fp32, weight (n,) = sel / (n_sel * d)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, weight):
+        from . import ops
+        ops.use_current_stream()
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        ops.masked_mse_fwd(pred, target, weight, loss)
+        ctx.save_for_backward(pred, target, weight)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        from . import ops
+        ops.use_current_stream()
+        pred, target, weight = ctx.saved_tensors
+        dpred = torch.empty_like(pred)
+        ops.masked_mse_bwd(pred, target, weight, dloss.to(torch.float32).contiguous(), dpred)
+        return dpred, None, None
+
+
+def masked_mse(pred, target, weight):
+    """sum_rows weight[row] * sum_f (pred - target)^2 on the device; CPU tensors (host-side tests of the step logic)
+    take the same expression in torch."""
+    if not pred.is_cuda:
+        diff = pred.float() - target
+        return (diff * diff * weight[:, None]).sum()
+    pred = pred if pred.dtype == torch.bfloat16 else pred.to(torch.bfloat16)
+    return _MaskedMse.apply(pred.contiguous(), target.contiguous(), weight.contiguous())
+
+
 def relation_loss(scores, pos_labels, sample_n, w_multi=1.0, w_bin=1.0):
     """xtrainer.py:2359-2372 / 1917-1942: CE over groups of sample_n + BCE against the one-hot positive."""
     ce = F.cross_entropy(scores.view(-1, sample_n), pos_labels)
@@ -40,7 +73,7 @@ def relation_loss(scores, pos_labels, sample_n, w_multi=1.0, w_bin=1.0):
 def pretrain_step(model, batch, sample_n=4, heads=("mlm", "mrm", "mrfr", "rel"), lambdas=None):
     """jointfwd + the selected heads + loss assembly (xtrainer.py:2281-2375).  `heads=("rel",)` is the
     fine-tune ITM step (t2i_step / i2t_step, :1911-1942).  Returns (total_loss, dict of losses)."""
-    lam = dict(mlm=1.0, mrm=1.0, mrfr=1.0, rel=1.0)
+    lam = dict(mlm=1.0, mrm=1.0, mrfr=1.0, rel=1.0, clcm=1.0)
     if lambdas:
         lam.update(lambdas)
     R = batch["x_img"].shape[0]
@@ -66,12 +99,19 @@ def pretrain_step(model, batch, sample_n=4, heads=("mlm", "mrm", "mrfr", "rel"),
         add("mrm", l)
     if "mrfr" in heads:
         reg = model("predict", tensor=img_out, is_mrfr=True)
-        diff = reg.reshape(-1, 2048).float() - batch["ori_feats"].reshape(-1, 2048)
         # == F.mse_loss(reg[sel], target[sel]) (:2334-2348) without the boolean gather
-        add("mrfr", (diff * diff * batch["mrfr_weight"][:, None]).sum())
+        add("mrfr", masked_mse(reg.reshape(-1, 2048), batch["ori_feats"].reshape(-1, 2048), batch["mrfr_weight"]))
     if "rel" in heads:
         scores = model("predict", tensor=enc.transpose(0, 1), is_relation=True)
         add("rel", relation_loss(scores, batch["pos_labels"], sample_n))
+    if "clcm" in heads:
+        # i2t branch (:2379-2393): a second jointfwd over the code-switched caption x2 with the SAME regions, the
+        # second pooler + classifier (is_clcm), BCE against clcm_labels; added to the total with weight 1
+        enc2 = model("jointfwd", x=batch["x2"], lengths=batch["lengths2"], x_img=batch["x_img"],
+                     lengths_img=batch["lengths_img"], causal=False, langs=None, image_loc=batch["image_loc"],
+                     refine_image=False)
+        scores2 = model("predict", tensor=enc2.transpose(0, 1), is_clcm=True)
+        add("clcm", F.binary_cross_entropy_with_logits(scores2.view(-1), batch["clcm_labels"].view(-1).to(scores2.dtype)))
     return total, losses
 
 
@@ -114,32 +154,100 @@ def mlm_step(model, x, lengths, pred_mask, y, positions=None, langs=None, lambda
     return lambda_coeff * loss
 
 
-def freelb_relation_step(model, batch, sample_n=4, adv_steps=3, adv_lr_text=1e-1, adv_lr_img=1e-1, max_norm=0.0):
-    """The FreeLB variant of the ITM fine-tune step (xtrainer.py:2021-2223, `--is_freelb`): `adv_steps` ascent
-    steps on perturbations of the token embeddings (`jointfwd(text_embed=...)`, :910-913) and of the region
-    features, accumulating the parameter gradients of every ascent step (averaged), as FreeLB does.  Uses the
-    input gradients d text_embed / d x_img the encoder backward provides.  Returns the mean loss."""
-    emb = model.embeddings.weight
-    x, R = batch["x"], batch["x_img"].shape[0]
-    base_text = torch.nn.functional.embedding(x.transpose(0, 1), emb.detach())        # (B, T, d) fp32
-    delta_t = torch.zeros_like(base_text)
-    delta_i = torch.zeros_like(batch["x_img"])
+def init_adv_delta(like, row_dims, adv_init_mag=1e-4, norm_type="l2", generator=None):
+    """Initial FreeLB perturbation (deal_freelb_delta / deal_image_freelb_delta, xtrainer.py:2700-2736): uniform in
+    [-1, 1] scaled per slice of dim 0 by adv_init_mag / sqrt(row_dims) ("l2"; row_dims = lengths * dim for the token
+    embeddings (B, T, d), the feature width for the (R, B, 2048) region features — the reference scales those per
+    region index, and so does this), or uniform in [-adv_init_mag, adv_init_mag] ("linf"); zeros when the magnitude
+    is 0."""
+    if adv_init_mag <= 0:
+        return torch.zeros_like(like)
+    if norm_type == "linf":
+        return torch.zeros_like(like).uniform_(-adv_init_mag, adv_init_mag, generator=generator)
+    if norm_type != "l2":
+        raise NotImplementedError("Norm type {} not specified.".format(norm_type))
+    noise = torch.zeros_like(like).uniform_(-1, 1, generator=generator)
+    mag = adv_init_mag / torch.sqrt(row_dims.to(torch.float32))
+    return (noise * mag.to(like.device).view(-1, *([1] * (like.dim() - 1)))).detach()
+
+
+def ascend_adv_delta(delta, delta_grad, adv_lr=1e-3, adv_max_norm=1e-2, norm_type="l2"):
+    """One ascent step on a FreeLB perturbation (update_freelb_delta / update_image_freelb_delta,
+    xtrainer.py:2793-2851): normalise the gradient per slice of dim 0, step by adv_lr, project back onto the
+    adv_max_norm ball (l2) or box (linf)."""
+    n0 = delta.size(0)
+    bshape = (n0,) + (1,) * (delta.dim() - 1)
+    g = delta_grad.detach()
+    if norm_type == "l2":
+        gn = g.reshape(n0, -1).norm(dim=1).clamp(min=1e-8).view(bshape)
+        delta = (delta.detach() + adv_lr * g / gn).detach()
+        if adv_max_norm > 0:
+            dn = delta.reshape(n0, -1).float().norm(p=2, dim=1)
+            over = (dn > adv_max_norm).to(delta.dtype)
+            delta = (delta * (adv_max_norm / dn * over + (1 - over)).view(bshape)).detach()
+    elif norm_type == "linf":
+        gn = g.reshape(n0, -1).norm(dim=1, p=float("inf")).clamp(min=1e-8).view(bshape)
+        delta = (delta.detach() + adv_lr * g / gn).detach()
+        if adv_max_norm > 0:
+            delta = delta.clamp(-adv_max_norm, adv_max_norm).detach()
+    else:
+        raise NotImplementedError("Norm type {} not specified.".format(norm_type))
+    return delta
+
+
+def freelb_relation_step(model, batch, sample_n=4, adv_steps=3, adv_init_mag=1e-4, adv_lr=1e-3, adv_max_norm=1e-2,
+                         norm_type="l2", optimizer=None, reducer=None, init=None, trace=None):
+    """FreeLB variant of the ITM fine-tune step (freelb_t2i_step / freelb_i2t_step, xtrainer.py:2021-2223,
+    `--is_freelb`): `adv_steps` ascent steps on perturbations of the token embeddings
+    (`jointfwd(text_embed=embeds_init + delta)`, transformer.py:910-913) and of the region features.  `embeds_init =
+    model.embeddings(ids)` stays attached to the graph, so the table is trained through it, and is looked up again
+    after every ascent step (:2820-2823).  Each step's loss is divided by adv_steps and back-propagated:
+      * optimizer given  — the reference's `free_optimize` without AMP (:2766-2776): zero_grad, backward, clip +
+        optimizer step at EVERY ascent step;
+      * optimizer = None — its AMP branch inside an accumulation window (:2789-2791): the parameter gradients of
+        the ascent steps accumulate in the flat buffer and the caller steps afterwards.
+    `reducer` (ddp.GradReducer): accumulated backwards run under `reducer.accumulate()`; `finish()` follows every
+    backward that is followed by an optimizer step, or the last one.  `init` = (delta_text, delta_img) overrides
+    the random initialisation (tests); `trace`, if a list, receives (loss, delta_text, delta_img) per step.
+    Returns the summed loss (a device scalar; the reference logs the same sum)."""
+    x = batch["x"]
+    ids = x.transpose(0, 1)
+    embeds_init = model.embeddings(ids)                                               # (B, T, d) fp32, :2700-2705
+    if init is not None:
+        delta_t, delta_i = init
+    else:
+        delta_t = init_adv_delta(embeds_init, batch["lengths"] * embeds_init.size(-1), adv_init_mag, norm_type)
+        rdims = torch.full((batch["x_img"].size(0),), float(batch["x_img"].size(-1)))
+        delta_i = init_adv_delta(batch["x_img"], rdims, adv_init_mag, norm_type)
     total = 0.0
-    for _ in range(adv_steps):
-        dt = delta_t.clone().requires_grad_(True)
-        di = delta_i.clone().requires_grad_(True)
-        enc = model("jointfwd", x=x, lengths=batch["lengths"], x_img=batch["x_img"] + di, lengths_img=batch["lengths_img"],
-                    causal=False, image_loc=batch["image_loc"], text_embed=base_text + dt)
+    for astep in range(adv_steps):
+        last = astep == adv_steps - 1
+        delta_t = delta_t.detach().requires_grad_(True)
+        delta_i = delta_i.detach().requires_grad_(True)
+        enc = model("jointfwd", x=x, lengths=batch["lengths"], x_img=batch["x_img"] + delta_i,
+                    lengths_img=batch["lengths_img"], causal=False, image_loc=batch["image_loc"],
+                    text_embed=delta_t + embeds_init)
         scores = model("predict", tensor=enc.transpose(0, 1), is_relation=True)
-        loss = relation_loss(scores, batch["pos_labels"], sample_n) / adv_steps
-        loss.backward()          # parameter gradients accumulate in the flat buffer; dt.grad / di.grad for the ascent
-        total = total + float(loss.detach())
-        for d_, g_, lr in ((delta_t, dt.grad, adv_lr_text), (delta_i, di.grad, adv_lr_img)):
-            gn = g_.flatten(1).norm(dim=1).clamp_min(1e-12).view(-1, *([1] * (g_.dim() - 1)))
-            d_.add_(lr * g_ / gn)                                                    # normalised ascent step
-            if max_norm > 0:
-                dn = d_.flatten(1).norm(dim=1).view(-1, *([1] * (d_.dim() - 1)))
-                d_.mul_((max_norm / dn.clamp_min(1e-12)).clamp(max=1.0))
+        loss = relation_loss(scores, batch["pos_labels"], sample_n) / (1.0 * adv_steps)
+        if optimizer is not None:
+            model.zero_grad()
+        if reducer is not None and optimizer is None and not last:
+            with reducer.accumulate():
+                loss.backward()
+        else:
+            loss.backward()
+            if reducer is not None:
+                reducer.finish()
+        if optimizer is not None:
+            optimizer.step()
+        total = total + loss.detach()
+        if trace is not None:
+            trace.append((loss.detach(), delta_t.detach(), delta_i.detach(), delta_t.grad, delta_i.grad))
+        if last:
+            break
+        delta_t = ascend_adv_delta(delta_t, delta_t.grad, adv_lr, adv_max_norm, norm_type)
+        delta_i = ascend_adv_delta(delta_i, delta_i.grad, adv_lr, adv_max_norm, norm_type)
+        embeds_init = model.embeddings(ids)                                           # :2820-2823
     return total
 
 
@@ -227,9 +335,28 @@ class GraphedStep:
         total, _ = pretrain_step(self.model, self.batch, self.sample_n, self.heads, self.lambdas)
         cur.wait_event(cleared)
         total.backward()
+        self._snapshot_touched()
         if self.after_backward is not None:
             self.after_backward()
         return total.detach()
+
+    def _snapshot_touched(self):
+        """The next zero_grad clears the token-embedding rows listed in model._emb_touched.  Those lists alias the
+        graph's static input tensors, which `step(new_batch)` overwrites before the next replay — the replayed clear
+        would then miss the rows the previous batch touched.  Copy the ids into persistent buffers INSIDE the step
+        (captured with it), so every replay clears exactly what its predecessor wrote."""
+        m = self.model
+        touched = m._emb_touched
+        if not touched:
+            return
+        if not hasattr(self, "_touched_bufs"):
+            self._touched_bufs = [torch.empty_like(t) for t in touched]
+        if len(self._touched_bufs) != len(touched) or any(b.shape != t.shape for b, t in zip(self._touched_bufs, touched)):
+            return  # different step shape (not reachable through this class): keep the aliasing lists
+        for b, t in zip(self._touched_bufs, touched):
+            if b.data_ptr() != t.data_ptr():
+                b.copy_(t)
+        m._emb_touched = list(self._touched_bufs)
 
     def release(self):
         """Drop the captured graph (needed before torch.distributed.destroy_process_group() when collectives

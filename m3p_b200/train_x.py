@@ -163,10 +163,13 @@ def main(params):
                     model.zero_grad()
                 dbatch = {k: v.to(dev, non_blocking=True) for k, v in batch.items()}
                 loss, _ = pretrain_step(model, dbatch, params.sample_n, heads, lambdas)
-                (loss / acc).backward()
-                loss = loss.detach()
                 if (n_iter + 1) % acc == 0:
+                    (loss / acc).backward()     # the last micro-step announces the (accumulated) slices to NCCL
                     reducer.finish()
+                else:
+                    with reducer.accumulate():  # earlier micro-steps must not send anything (ddp.GradReducer.accumulate)
+                        (loss / acc).backward()
+                loss = loss.detach()
             if (n_iter + 1) % acc == 0:
                 optimizer.step()  # clip + Adam + bf16 operand refresh + gradient clear (xtrainer.py:222-228)
             n_iter += 1

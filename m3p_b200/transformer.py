@@ -43,7 +43,8 @@ def get_masks(slen, lengths, causal, k=None):
     """Hidden-state mask (and the identical attention mask) — transformer.py:59-78, non-causal."""
     if causal:
         raise NotImplementedError("causal masks are outside the B200 encoder training path")
-    assert lengths.max().item() <= slen
+    if not lengths.is_cuda:  # the reference's check (:63); on the device it would cost a host sync per call
+        assert lengths.max().item() <= slen
     alen = torch.arange(slen, dtype=torch.long, device=lengths.device)
     mask = alen < lengths[:, None]
     return mask, mask
@@ -51,6 +52,15 @@ def get_masks(slen, lengths, causal, k=None):
 
 class _Node(nn.Module):
     """Name-space holder so parameters register under the reference's dotted names."""
+
+
+class _EmbeddingNode(_Node):
+    """`model.embeddings` — callable like the reference's nn.Embedding(n_words, dim, padding_idx)
+    (transformer.py:21-26, 658): `model.embeddings(input_ids)` is what FreeLB builds `embeds_init` from
+    (xtrainer.py:2700-2705, 2820-2823), attached to the graph so the table is trained through it."""
+
+    def forward(self, input_ids):
+        return _EmbedLookupFn.apply(self.weight, input_ids, self.__dict__["_owner"]())
 
 
 def _align(n, a=64):
@@ -114,6 +124,7 @@ class TransformerModel(nn.Module):
         self._emb_dense_dirty = True  # True once a dense update (tied MLM head) or foreign writer touched it
         self._defer_token_grads = False      # set by ddp.GradReducer (world > 1): see _encode_backward
         self._deferred_token_grads = []      # [(token ids (T,B), per-position gradient (B,T,d) fp32)]
+        self._bwd_trace = None  # a list here makes _encode_backward record its intermediates (stage-parity tests)
         self.overlap_grads = os.environ.get("M3P_SIDE_STREAM", "1") != "0"
         self._side_streams = {}
         # set by m3p_b200.optim after a fused step (which also writes the bf16 operand copies and zeroes the
@@ -194,7 +205,13 @@ class TransformerModel(nn.Module):
         node = self
         for p in parts[:-1]:
             if not hasattr(node, p):
-                node.add_module(p, _Node())
+                if node is self and p == "embeddings":
+                    import weakref
+                    emb_node = _EmbeddingNode()
+                    emb_node.__dict__["_owner"] = weakref.ref(self)
+                    node.add_module(p, emb_node)
+                else:
+                    node.add_module(p, _Node())
             node = getattr(node, p)
         node.register_parameter(parts[-1], param)
 
@@ -726,6 +743,9 @@ class TransformerModel(nn.Module):
             ops.dgrad(dqkv, w["wqkv"], dhp, epi=L.M3P_EPI_DROP_RES, aux=dx1, out_f32=True)
             # the side stream may still be reading these: keep them alive until the join one layer later
             sq.close("layer%d" % i, self._segments["layer%d" % i], (dh, s, dx2, dx2d, du, dh1, dx1, dx1d, dqkv))
+            if self._bwd_trace is not None:  # tests only: every intermediate of this layer's backward, for stage parity
+                self._bwd_trace.append(dict(layer=i, stash=s, dh=dh, dx2=dx2, dx2d=dx2d, du=du, dh1=dh1, dx1=dx1,
+                                            dx1d=dx1d, dctx=dctx, dqkv=dqkv, dhp=dhp))
             dh = dhp
             st["layers"][i] = None
             del s, du, dx2, dx2d, dh1, dx1, dx1d, dqkv, dctx
@@ -752,10 +772,12 @@ class TransformerModel(nn.Module):
             if want_dtext:
                 d_text = e(B, T, d, dt=_F32)
                 b.d_text_embed = d_text.data_ptr()
-            elif self._defer_token_grads and self._emb_dense_dirty and "positions" not in st:
+            elif self._defer_token_grads and self._emb_dense_dirty:
                 # data-parallel step with the tied MLM head: the dense head contribution to d E is already being
                 # all-reduced (ddp.GradReducer sent it when the heads finished), so the gather's contribution must not
                 # be scattered into that buffer now — keep it per position and let the reducer exchange it as rows
+                # (position / language gradients are routed to their own tables independently of d_text_embed, so
+                # reset `positions` — the xMLM / TLM step — take this path too)
                 g_pos = e(B, T, d, dt=_F32)
                 b.d_text_embed = g_pos.data_ptr()
                 self._deferred_token_grads.append((st["x"], g_pos))
@@ -869,6 +891,32 @@ class _EncoderFn(torch.autograd.Function):
         d_ximg, d_text = model._encode_backward(st, dh, want_img, want_txt)
         ctx.st = None
         return None, d_ximg, d_text, None, None, None, None
+
+
+class _EmbedLookupFn(torch.autograd.Function):
+    """Token-embedding lookup on its own, fp32 in / fp32 out; backward scatter-adds into the flat embedding gradient
+    (padding_idx rows get none, as nn.Embedding's)."""
+
+    @staticmethod
+    def forward(ctx, weight, ids, model):
+        model._require_cuda(ids)
+        ops.use_current_stream()
+        idx = ids.contiguous()
+        out = torch.empty(*idx.shape, weight.shape[1], dtype=_F32, device=weight.device)
+        ops.gather_rows_f32(weight.data, idx.view(-1), out, idx.numel(), weight.shape[1])
+        ctx.model, ctx.idx = model, idx
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        model, idx = ctx.model, ctx.idx
+        ops.use_current_stream()
+        model.attach_grads()
+        gc = g.to(_F32).contiguous()
+        ops.scatter_add_rows_f32(gc, idx.view(-1), model.pad_index, model._emb_grad, idx.numel(), gc.shape[-1])
+        if model._emb_touched is not None:
+            model._emb_touched.append(idx)
+        return None, None, None
 
 
 def _rows_of(tensor):

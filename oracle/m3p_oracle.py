@@ -232,6 +232,11 @@ def relation_loss(scores, pos_labels, sample_n, w_multi=1.0, w_bin=1.0):
     return w_multi * ce + w_bin * bce
 
 
+def clcm_loss(scores, clcm_labels):
+    """xtrainer.py:2389-2391: BCE of the second pass's is_clcm scores against clcm_labels."""
+    return F.binary_cross_entropy_with_logits(scores.view(-1), clcm_labels.view(-1).float())
+
+
 def pretrain_step_losses(sd, n_layers, n_heads, batch, sample_n, heads=("mlm", "mrm", "mrfr", "rel")):
     """One multitask step (xtrainer.py:2281-2375) on a batch dict with keys
     x, lengths, x_img, lengths_img, image_loc, x_labels (T,B), obj_labels (B,R), ori_feats (B,R,2048),

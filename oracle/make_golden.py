@@ -49,6 +49,42 @@ def build_reference(p, seed=0):
     return m
 
 
+# the new cases keep a representative subset of the gradients (fixtures stay small): the embedding tables, the
+# LayerNorms, one matrix and one bias of the first / last layer, the heads they exercise
+KEEP_GRADS = ("embeddings.weight", "position_embeddings.weight", "cross_lang_embeddings.weight", "layer_norm_emb.weight",
+              "layer_norm_emb.bias", "attentions.0.q_lin.weight", "attentions.0.k_lin.bias", "attentions.1.out_lin.weight",
+              "layer_norm1.0.weight", "ffns.1.lin2.bias", "ffns.0.lin1.bias", "layer_norm2.1.weight", "layer_norm2.1.bias",
+              "pred_layer.proj.bias", "pooled_layer.dense.weight", "pooled_layer.dense.bias", "seq_relationship.weight",
+              "seq_relationship.bias", "pooled_layer2.dense.weight", "pooled_layer2.dense.bias", "seq_relationship2.weight",
+              "seq_relationship2.bias", "image_embeddings.image_embeddings.bias", "image_embeddings.LayerNorm.weight",
+              "image_embeddings.image_location_embeddings.weight")
+
+
+def kept_grads(m):
+    """(subset of gradients, names of every parameter that received a non-zero gradient)."""
+    live = sorted(n for n, p_ in m.named_parameters() if p_.grad is not None and float(p_.grad.abs().max()) > 0)
+    return {n: dict(m.named_parameters())[n].grad.detach().clone() for n in live if n in KEEP_GRADS}, live
+
+
+def import_xtrainer():
+    """The reference trainer module with `apex` stubbed (it is imported at module level, xtrainer.py:24, and absent
+    here) and Tensor.cuda() made the identity: lets the generator call the trainer's own pure-torch helpers on CPU."""
+    import types
+    if "apex" not in sys.modules:
+        apex = types.ModuleType("apex")
+        apex.parallel = types.ModuleType("apex.parallel")
+        apex.parallel.DistributedDataParallel = type("DistributedDataParallel", (), {})
+        sys.modules["apex"], sys.modules["apex.parallel"] = apex, apex.parallel
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import src.xtrainer as X
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    return X
+
+
 def run_case(name, emb_dim, n_layers, n_heads, n_words, B, T, R, n_langs, ragged, seed):
     p = ref_params(emb_dim, n_layers, n_heads, n_words, n_langs)
     m = build_reference(p, seed)
@@ -101,6 +137,80 @@ def run_case(name, emb_dim, n_layers, n_heads, n_words, B, T, R, n_langs, ragged
                              image_loc=batch["image_loc"])
         out["crossfwd_img"] = m("crossfwd", x=batch["x_img"], lengths=batch["lengths_img"], causal=False, stream_="img",
                                 langs=None, cross_modal=True, image_loc=batch["image_loc"])
+
+    # ---- text-stream BACKWARD (mlm_step, xtrainer.py:734-770): fwd / crossfwd (+ positions, + langs) -> MLM head ->
+    #      loss.backward(); every gradient incl. cross_lang_embeddings (transformer.py:1056-1057) ----
+    gpos = torch.Generator().manual_seed(seed + 5)
+    positions = torch.stack([torch.randperm(T, generator=gpos) for _ in range(B)], dim=1)   # (T, B), reset positions
+    out["positions"] = positions
+    text_cases = {"fwd": dict(mode="fwd"), "crossfwd": dict(mode="crossfwd", stream_="text"),
+                  "crossfwd_positions": dict(mode="crossfwd", stream_="text", positions=positions)}
+    if n_langs > 1:
+        text_cases["crossfwd_langs"] = dict(mode="crossfwd", stream_="text", langs=out["langs"])
+        text_cases["crossfwd_langs_positions"] = dict(mode="crossfwd", stream_="text", langs=out["langs"],
+                                                      positions=positions)
+    out["text_bwd"] = {}
+    wsum = torch.randn(T, B, emb_dim, generator=torch.Generator().manual_seed(seed + 6))
+    out["text_bwd_weight"] = wsum
+    for cname, kw in text_cases.items():
+        kw = dict(kw)
+        mode = kw.pop("mode")
+        m.zero_grad()
+        t = m(mode, x=batch["x"], lengths=batch["lengths"], causal=False, **kw)
+        _, loss = m("predict", tensor=t, pred_mask=pm_text, y=y_text, get_scores=False)
+        tot = loss + 0.01 * (t * wsum).sum()           # the weighted sum reaches every row, not only the masked ones
+        tot.backward()
+        gr, live = kept_grads(m)
+        out["text_bwd"][cname] = dict(out=t.detach().clone(), loss=loss.item(), total=tot.item(), grads=gr, live=live)
+    m.zero_grad()
+
+    # ---- CLCM second pass (pretrain_under_step, i2t branch, xtrainer.py:2379-2393): jointfwd on the code-switched
+    #      caption x2 with the SAME regions -> predict(is_clcm=True) -> BCE against clcm_labels ----
+    b2 = O.synthetic_batch(B, T, R, n_words, sample_n=sample_n, seed=seed + 200, ragged=ragged, n_mask_text=3, n_mask_img=2)
+    clcm_labels = torch.randint(0, 2, (B,), generator=torch.Generator().manual_seed(seed + 7))
+    enc2 = m("jointfwd", x=b2["x"], lengths=b2["lengths"], x_img=batch["x_img"], lengths_img=batch["lengths_img"],
+             causal=False, langs=None, image_loc=batch["image_loc"], refine_image=False)
+    scores2 = m("predict", tensor=enc2.transpose(0, 1), is_clcm=True)
+    bce2 = F.binary_cross_entropy_with_logits(scores2.view(-1), clcm_labels.view(-1).float())
+    bce2.backward()
+    gr, live = kept_grads(m)
+    out["clcm"] = dict(x2=b2["x"], lengths2=b2["lengths"], clcm_labels=clcm_labels, scores=scores2.detach().clone(),
+                       loss=bce2.item(), grads=gr, live=live)
+    m.zero_grad()
+
+    # ---- FreeLB (freelb_t2i_step / freelb_i2t_step, xtrainer.py:2021-2223) with the reference's own delta helpers
+    #      (deal_freelb_delta / update_freelb_delta / deal_image_freelb_delta / update_image_freelb_delta,
+    #      :2700-2851) called through a stub `self`; no optimizer step between the ascent steps (the AMP
+    #      accumulate branch of free_optimize, :2778-2791), so gradients of the three steps accumulate ----
+    X = import_xtrainer()
+    stub = object.__new__(X.XTrainer)
+    torch.manual_seed(seed + 8)
+    x1 = batch["x"]
+    embeds_init, delta = X.XTrainer.deal_freelb_delta(stub, m, x1.transpose(0, 1), batch["lengths"])
+    image_delta = X.XTrainer.deal_image_freelb_delta(stub, batch["x_img"])
+    fl = dict(delta0=delta.clone(), image_delta0=image_delta.clone(), steps=[])
+    adv_steps = 3
+    for astep in range(adv_steps):
+        delta.requires_grad_()
+        text_imb = delta + embeds_init
+        image_delta.requires_grad_()
+        img_imb = batch["x_img"] + image_delta
+        enc_f = m("jointfwd", x=x1, lengths=batch["lengths"], x_img=img_imb, lengths_img=batch["lengths_img"], causal=False,
+                  langs=None, image_loc=batch["image_loc"], refine_image=False, text_embed=text_imb)
+        rs = m("predict", tensor=enc_f.transpose(0, 1), is_relation=True)
+        ce_f = F.cross_entropy(rs.view(-1, sample_n), batch["pos_labels"])
+        bce_f = F.binary_cross_entropy_with_logits(rs.view(-1), F.one_hot(batch["pos_labels"], sample_n).float().view(-1))
+        loss_f = (ce_f + bce_f) / (1.0 * adv_steps)
+        loss_f.backward()
+        rec = dict(loss=loss_f.item(), delta_grad=delta.grad.detach().clone(), image_delta_grad=image_delta.grad.detach().clone())
+        if astep < adv_steps - 1:
+            embeds_init, delta = X.XTrainer.update_freelb_delta(stub, m, delta, embeds_init, x1.transpose(0, 1))
+            image_delta = X.XTrainer.update_image_freelb_delta(stub, batch["x_img"], image_delta)
+            rec.update(delta_next=delta.clone(), image_delta_next=image_delta.clone())
+        fl["steps"].append(rec)
+    fl["grads"], fl["live"] = kept_grads(m)
+    out["freelb"] = fl
+    m.zero_grad()
     sd = m.state_dict()
     out["state_dict"] = {k: v.clone() for k, v in sd.items()
                          if not k.startswith(("refine_embeddings", "cross_alignment", "encoder_attn", "layer_norm15",

@@ -145,3 +145,33 @@ def test_recall_at_k_counts_like_the_reference():
     lab = torch.tensor([[1, 0, 0, 0], [0, 0, 0, 1]])
     i2t, t2i = recall_at_k(sc, lab, ks=(1, 2, 3))
     assert i2t == {1: 0.5, 2: 0.5, 3: 1.0} and t2i == {1: 0.5, 2: 0.5, 3: 0.5}
+
+
+def test_state_dict_names_and_shapes_equal_the_reference(golden_dir):
+    """Boundary (b): a reference checkpoint loads unchanged — TransformerModel.state_dict() has exactly the keys
+    and shapes the reference module has (tests/golden/state_dict_keys.json, written by oracle/make_golden.py from
+    the reference class), for both fixture configurations."""
+    import argparse
+    import json
+    from m3p_b200.transformer import TransformerModel
+    want = json.load(open(os.path.join(golden_dir, "state_dict_keys.json")))
+    for case, (d, n_words, n_langs) in (("c1_tiny", (128, 1000, 1)), ("c1_ragged_langs", (128, 600, 3))):
+        langs = ["en", "fr", "de", "zh"][:n_langs]
+        ns = argparse.Namespace(
+            n_langs=n_langs, n_words=n_words, eos_index=2, pad_index=1, id2lang=dict(enumerate(langs)),
+            lang2id={l: i for i, l in enumerate(langs)}, emb_dim=d, n_heads=2, n_layers=2, n_dec_layers=2, dropout=0.0,
+            attention_dropout=0.0, sinusoidal_embeddings=False, refine_layers=1, attention_setting="v1",
+            use_externel_att=False, gelu_activation=True, share_inout_emb=True, asm=False)
+        m = TransformerModel(ns, is_encoder=True, with_output=True, is_crossModal=True)
+        got = {k: list(v.shape) for k, v in m.state_dict().items()}
+        assert got == want[case], sorted(set(got) ^ set(want[case]))
+
+
+def test_get_masks_on_cpu():
+    """E0 on CPU: the product's get_masks equals the reference's non-causal masks (transformer.py:59-78)."""
+    import torch
+    from m3p_b200.transformer import get_masks
+    mask, attn = get_masks(5, torch.tensor([3, 0, 5]), False)
+    assert mask.tolist() == [[True] * 3 + [False] * 2, [False] * 5, [True] * 5] and attn is mask
+    with pytest.raises(AssertionError):
+        get_masks(4, torch.tensor([5]), False)

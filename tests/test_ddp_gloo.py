@@ -162,3 +162,54 @@ def test_single_process_is_a_noop():
     assert m._grad_ready_hook is None
     red.finish()
     assert torch.equal(m._flat_grad, before)
+
+
+def _worker_accumulate(rank, world, port, q):
+    """Gradient accumulation (`--accumulate_gradients 2`, FreeLB's ascent steps): micro-step 1 runs under
+    reducer.accumulate() — its hooks send nothing — micro-step 2 adds local gradients to the same buffers and
+    announces the slices; every slice must end up averaged exactly once, with both micro-steps inside."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from m3p_b200.ddp import GradReducer
+    m = _FakeModel(rank)
+    m._emb_touched, m._emb_dense_dirty, m._deferred_token_grads = None, True, []
+    red = GradReducer(m)
+    step1 = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    step2 = torch.ones(1000) * (10.0 * (rank + 1))
+    m._flat_grad = step1.clone()
+    with red.accumulate():
+        assert not m._defer_token_grads
+        for name in ("heads", "layer1", "layer0"):
+            m._grad_ready_hook(name, *m._segments[name])
+    ok = torch.equal(m._flat_grad, step1) and not red._works and not red._done and m._defer_token_grads
+    m._flat_grad += step2                                    # the second backward accumulates on top
+    for name in ("heads", "layer1", "layer0"):
+        m._grad_ready_hook(name, *m._segments[name])
+    red.finish()
+    mean = sum(range(1, world + 1)) / world
+    want = torch.arange(1000, dtype=torch.float32) * mean + 10.0 * mean
+    ok = ok and torch.allclose(m._flat_grad, want)
+    # entering accumulate() after something was already sent is a usage error, not silent corruption
+    m._grad_ready_hook("heads", *m._segments["heads"])
+    try:
+        with red.accumulate():
+            pass
+        ok = False
+    except RuntimeError:
+        pass
+    red.finish()
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gradient_accumulation_sends_nothing_until_the_last_backward_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_accumulate, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res

@@ -137,3 +137,93 @@ def test_rounding_matched_mode_stays_close_to_the_reference(golden_dir, name):
     lengths = batch["lengths"] + batch["lengths_img"]
     pad = torch.arange(S)[:, None] >= lengths[None, :]
     assert float(enc.detach()[pad].abs().max()) == 0.0 if bool(pad.any()) else True
+
+
+# ---------------------------------------------------------------------------------------------------
+# text-stream backward, CLCM second pass, FreeLB: fixtures generated from the reference's own code
+# ---------------------------------------------------------------------------------------------------
+def _leaf(sd):
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "pred_layer.proj.weight"}
+    leaf["pred_layer.proj.weight"] = leaf["embeddings.weight"]
+    return leaf
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_text_stream_backward_matches_reference(golden_dir, name):
+    """mlm_step's path (xtrainer.py:734-770): fwd / crossfwd (+ reset positions, + langs) -> MLM head -> backward;
+    outputs, losses and the gradients of the embedding tables (cross_lang_embeddings included), layer_norm_emb and
+    the layers against the reference's."""
+    g, sd = _load(golden_dir, name)
+    cfg, batch = g["config"], g["batch"]
+    L, H = cfg["n_layers"], cfg["n_heads"]
+    y_text, pm = O.get_mask_(batch["x_labels"])
+    for cname, ref in g["text_bwd"].items():
+        leaf = _leaf(sd)
+        kw = dict(positions=g["positions"] if "positions" in cname else None)
+        if cname == "fwd":
+            t = O.fwd_text(leaf, L, H, batch["x"], batch["lengths"])
+        else:
+            t = O.crossfwd_text(leaf, L, H, batch["x"], batch["lengths"], langs=g["langs"] if "langs" in cname else None, **kw)
+        _, loss = O.predict_mlm(leaf, t, pm, y_text)
+        tot = loss + 0.01 * (t * g["text_bwd_weight"]).sum()
+        tot.backward()
+        assert _close(t.detach(), ref["out"]), cname
+        assert abs(loss.item() - ref["loss"]) < 1e-5 * abs(ref["loss"]), cname
+        live = sorted(k for k, v in leaf.items() if v.grad is not None and float(v.grad.abs().max()) > 0
+                      and k != "pred_layer.proj.weight")
+        assert live == [k for k in ref["live"] if k != "pred_layer.proj.weight"], cname
+        for k, gr in ref["grads"].items():
+            assert _close(leaf[k].grad, gr, 1e-4), (cname, k)
+        assert ("cross_lang_embeddings.weight" in ref["grads"]) == ("langs" in cname)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_clcm_second_pass_matches_reference(golden_dir, name):
+    g, sd = _load(golden_dir, name)
+    cfg, batch, c = g["config"], g["batch"], g["clcm"]
+    leaf = _leaf(sd)
+    enc2 = O.jointfwd(leaf, cfg["n_layers"], cfg["n_heads"], c["x2"], c["lengths2"], batch["x_img"], batch["lengths_img"],
+                      batch["image_loc"])
+    scores = O.predict_relation(leaf, enc2.transpose(0, 1), clcm=True)
+    loss = O.clcm_loss(scores, c["clcm_labels"])
+    loss.backward()
+    assert _close(scores.detach(), c["scores"]) and abs(loss.item() - c["loss"]) < 1e-5 * abs(c["loss"])
+    for k, gr in c["grads"].items():
+        assert _close(leaf[k].grad, gr, 1e-4), k
+    assert leaf["pooled_layer.dense.weight"].grad is None  # the ITM pooler is not on this pass
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_freelb_helpers_and_trajectory_match_reference(golden_dir, name):
+    """The FreeLB perturbation helpers (train_step.init_adv_delta / ascend_adv_delta: host-side tensor prep, run here
+    on CPU) reproduce the reference's deal_* / update_* functions bit for bit given the same RNG state, and the
+    oracle reproduces the three ascent steps (losses, perturbation gradients, accumulated parameter gradients —
+    the token table included, which is trained through embeds_init)."""
+    from m3p_b200.train_step import ascend_adv_delta, init_adv_delta
+    g, sd = _load(golden_dir, name)
+    cfg, batch, fl = g["config"], g["batch"], g["freelb"]
+    seed = {"c1_tiny.pt": 0, "c1_ragged_langs.pt": 7}[name]
+    B, T, R, d = cfg["B"], cfg["T"], cfg["R"], cfg["emb_dim"]
+    torch.manual_seed(seed + 8)
+    d0 = init_adv_delta(torch.zeros(B, T, d), batch["lengths"] * d)
+    i0 = init_adv_delta(batch["x_img"], torch.full((R,), 2048.0))
+    assert torch.equal(d0, fl["delta0"]) and torch.equal(i0, fl["image_delta0"])
+    leaf = _leaf(sd)
+    delta_t, delta_i = d0, i0
+    for s, rec in enumerate(fl["steps"]):
+        delta_t = delta_t.detach().requires_grad_(True)
+        delta_i = delta_i.detach().requires_grad_(True)
+        emb = torch.nn.functional.embedding(batch["x"].transpose(0, 1), leaf["embeddings.weight"], padding_idx=1)
+        enc = O.jointfwd(leaf, cfg["n_layers"], cfg["n_heads"], batch["x"], batch["lengths"], batch["x_img"] + delta_i,
+                         batch["lengths_img"], batch["image_loc"], text_embed=emb + delta_t)
+        loss = O.relation_loss(O.predict_relation(leaf, enc.transpose(0, 1)), batch["pos_labels"], cfg["sample_n"]) / 3.0
+        loss.backward()
+        assert abs(loss.item() - rec["loss"]) < 1e-5 * abs(rec["loss"]), s
+        assert _close(delta_t.grad, rec["delta_grad"], 1e-4) and _close(delta_i.grad, rec["image_delta_grad"], 1e-4)
+        if "delta_next" in rec:
+            assert torch.equal(ascend_adv_delta(delta_t, rec["delta_grad"]), rec["delta_next"])
+            assert torch.equal(ascend_adv_delta(delta_i, rec["image_delta_grad"]), rec["image_delta_next"])
+            delta_t, delta_i = rec["delta_next"], rec["image_delta_next"]
+    for k, gr in fl["grads"].items():
+        assert _close(leaf[k].grad, gr, 1e-4), k
+    assert "embeddings.weight" in fl["grads"]
