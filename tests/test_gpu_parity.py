@@ -2,12 +2,17 @@
 the unmodified reference and (b) the CPU/torch oracle restatement, plus size-independent properties
 at BASELINE.json's full sizes.  Every test here needs a B200: `pytest -m gpu`.
 
-Stated tolerances: the kernels round tensor-core operands to bf16 and keep accumulation,
-softmax, LayerNorm statistics and losses in fp32.  Against the fp32 reference that gives ~2e-3 relative
-(L2) per kernel and <= ~1e-2 on encoder outputs / weight gradients after 2-12 layers — the same order
-as the reference's own bf16-autocast deviation from its fp32 run (4.6e-3 outputs, 5-8e-3 grads,
-BASELINE.md §4).  Bounds asserted below: single kernels 1e-2, end-to-end outputs 2e-2, gradients 5e-2,
-losses 2e-2 relative; padded rows exactly 0.
+Stated tolerances (north_star: 1e-3 relative).  Tensor-core operands are bf16; accumulation, softmax,
+LayerNorm statistics, the WHOLE residual stream (forward and backward) and losses are fp32.
+  * per kernel / stage, on that stage's own inputs, vs the reference expression with bf16 rounding at the same points:
+    asserted < 1e-3 for every forward and every backward stage (measured <= 8e-5).
+  * single kernels vs fp32 torch on bf16 inputs: 5e-3 (one bf16 rounding of the output is 2e-3 by itself).
+  * end to end vs the fp32 reference: outputs 6e-3, gradients 1.2e-2, losses 2e-3 on the golden fixtures and the
+    2-4-layer oracle runs; at BASELINE's full size (12 layers, 64 pairs, V = 250 002) outputs and every checked
+    gradient < 8e-3 AND no worse than the reference's own bf16-autocast deviation measured in the same test
+    (measured: 3.6e-3 / worst gradient 7.5e-3, autocast 4.4e-3 / 4.2e-2).  The 2-pair fixture (c1_tiny) gets 3e-2 on
+    gradients: with two samples a bias gradient is a difference of two nearly equal terms.
+  * padded rows exactly 0; integer / index work exact.
 """
 import argparse
 import os
@@ -18,7 +23,12 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-KERNEL_TOL, OUT_TOL, GRAD_TOL, LOSS_TOL = 1e-2, 2e-2, 5e-2, 2e-2
+KERNEL_TOL, OUT_TOL, GRAD_TOL, LOSS_TOL = 5e-3, 6e-3, 1.2e-2, 2e-3
+GRAD_TOL_TINY = 3e-2  # the 2-pair fixture
+
+
+def _gtol(cfg):
+    return GRAD_TOL_TINY if cfg["B"] < 4 else GRAD_TOL
 
 
 def _rel(got, ref):
@@ -262,14 +272,14 @@ def test_jointfwd_heads_and_every_gradient_match_the_reference(m3p, golden_dir, 
         assert float(enc.detach().float().cpu()[pad].abs().max()) == 0.0
     for k in ("mlm", "mrm", "mrfr", "rel"):
         assert abs(float(losses[k].detach()) - ref["losses"][k]) < LOSS_TOL * abs(ref["losses"][k]), k
-    assert _rel(batch["x_img"].grad, ref["grad_x_img"]) < GRAD_TOL
+    assert _rel(batch["x_img"].grad, ref["grad_x_img"]) < _gtol(cfg)
     named = dict(model.named_parameters(remove_duplicate=False))
     checked = 0
     for k, gr in ref["grads"].items():
         if k == "pred_layer.proj.weight" or gr.norm() < 1e-7:
             continue
         assert named[k].grad is not None, k
-        assert _rel(named[k].grad, gr) < GRAD_TOL, k
+        assert _rel(named[k].grad, gr) < _gtol(cfg), k
         checked += 1
     assert checked > 40
     # parameters the reference leaves without gradient stay without one (or exactly zero in the flat buffer)
@@ -355,7 +365,7 @@ def test_text_stream_backward_matches_the_reference(m3p, golden_dir, name):
                 assert float(named[k].grad.norm()) < 1e-3, (cname, k)
                 continue
             worst[cname + ":" + k] = _rel(named[k].grad, gr)
-            assert worst[cname + ":" + k] < GRAD_TOL, (cname, k, worst[cname + ":" + k])
+            assert worst[cname + ":" + k] < _gtol(cfg), (cname, k, worst[cname + ":" + k])
         for k in ("pooled_layer.dense.weight", "image_embeddings.image_embeddings.weight"):
             assert named[k].grad is None or float(named[k].grad.abs().max()) == 0.0
         if "langs" not in cname and "cross_lang_embeddings.weight" in named:
@@ -381,7 +391,7 @@ def test_clcm_second_pass_matches_the_reference(m3p, golden_dir, name):
     named = dict(model.named_parameters(remove_duplicate=False))
     for k, gr in c["grads"].items():
         if gr.norm() >= 1e-7:
-            assert _rel(named[k].grad, gr) < GRAD_TOL, k
+            assert _rel(named[k].grad, gr) < _gtol(cfg), k
     assert float(named["pooled_layer.dense.weight"].grad.abs().max()) == 0.0
     with torch.no_grad():
         enc2 = model("jointfwd", x=batch["x2"], lengths=batch["lengths2"], x_img=batch["x_img"], lengths_img=batch["lengths_img"],
@@ -420,13 +430,13 @@ def test_freelb_step_matches_the_reference(m3p, golden_dir, name):
     assert abs(float(total) - sum(r["loss"] for r in fl["steps"])) < LOSS_TOL * abs(float(total))
     for s, (rec, (loss, dt, di, gt, gi)) in enumerate(zip(fl["steps"], trace)):
         assert abs(float(loss) - rec["loss"]) < LOSS_TOL * abs(rec["loss"]), s
-        assert _rel(gt, rec["delta_grad"]) < GRAD_TOL and _rel(gi, rec["image_delta_grad"]) < GRAD_TOL, s
+        assert _rel(gt, rec["delta_grad"]) < _gtol(cfg) and _rel(gi, rec["image_delta_grad"]) < _gtol(cfg), s
         if "delta_next" in rec:
-            assert _rel(trace[s + 1][1], rec["delta_next"]) < GRAD_TOL and _rel(trace[s + 1][2], rec["image_delta_next"]) < GRAD_TOL
+            assert _rel(trace[s + 1][1], rec["delta_next"]) < _gtol(cfg) and _rel(trace[s + 1][2], rec["image_delta_next"]) < _gtol(cfg)
     named = dict(model.named_parameters(remove_duplicate=False))
     for k, gr in fl["grads"].items():
         if gr.norm() >= 1e-7:
-            assert _rel(named[k].grad, gr) < GRAD_TOL, k
+            assert _rel(named[k].grad, gr) < _gtol(cfg), k
     # the optimizer variant (free_optimize without AMP: a full update at every ascent step) trains
     from m3p_b200 import optim
     opt = optim.get_optimizer([p for p in model.parameters() if p.requires_grad], "adam,lr=0.002")
@@ -696,9 +706,9 @@ def test_end_to_end_against_rounding_matched_and_fp32_oracle(m3p):
                        "grads": grads, "worst_grad": max(grads.values())}
     _dump("parity_table.json", table)
     m = table["matched"]
-    assert m["encoder_out"] < 1e-2 and m["mlm_logits"] < 1e-2, m
+    assert m["encoder_out"] < 5e-3 and m["mlm_logits"] < 5e-3, m
     assert all(v < 1e-3 for v in m["losses"].values()), m["losses"]
-    assert m["worst_grad"] < 2e-2, m["grads"]
+    assert m["worst_grad"] < GRAD_TOL, m["grads"]
     assert table["fp32"]["encoder_out"] < OUT_TOL and table["fp32"]["worst_grad"] < GRAD_TOL
 
 
