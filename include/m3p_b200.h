@@ -202,7 +202,13 @@ typedef struct m3p_ln_bwd_args {
   float* dbias;
   int64_t rows, d;
   int32_t x_f32, dy_f32, dx_f32;
+  /* optional fp32 scratch of M3P_LN_BWD_SCRATCH_FLOATS(d) floats: with it the row pass also accumulates the column
+   * sums (dy, x and dx_drop are read once instead of twice) into per-CTA partials stored here, and the column pass
+   * (m3p_layernorm_bwd_cols, possibly on another stream) only adds those partials into dgamma / dbeta / dbias.
+   * The buffer must stay untouched between the two calls.  NULL keeps the two independent passes. */
+  float* col_scratch;
 } m3p_ln_bwd_args;
+#define M3P_LN_BWD_SCRATCH_FLOATS(d) (512 * 3 * (d))
 M3P_API int m3p_layernorm_bwd(const m3p_ln_bwd_args* args, m3p_stream_t stream);
 /* The two passes of m3p_layernorm_bwd on their own, so a caller can put the parameter-gradient column
  * pass (dgamma / dbeta / dbias; reads dy, x, mean, rstd and the dx / dx_drop the row pass wrote) on a

@@ -3,6 +3,8 @@
 // fp32->bf16 casts, gather / scatter of token rows, cross-entropy forward+backward, tiny linears.
 // One warp owns one row; 16-byte vector loads; warp-shuffle reductions; no shared-memory staging
 // (every element is touched once).  Grids are sized as multiples of the SM count.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -125,6 +127,115 @@ ln_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ gamma,
   }
 }
 
+// Row-pipelined LayerNorm forward for the encoder's big launches: one CTA of 12 warps per SM, every warp streams its
+// rows through a private ring of shared-memory stages filled by 1-D bulk copies (cp.async.bulk, completion on the
+// warp's own mbarriers).  A warp-per-row kernel that loads straight into registers has one row per warp in flight
+// and alternates between waiting and computing; here up to LNP_STAGES rows per warp (>= 100 KB per SM) are in flight
+// while the previous row is being normalised, which is what a ~25 us HBM-bound launch needs on a B200.
+constexpr int LNP_WARPS = 12;
+constexpr int LNP_THREADS = LNP_WARPS * 32;
+constexpr int LNP_MAX_STAGES = 4;
+constexpr uint32_t LNP_SMEM_BUDGET = 216 * 1024;
+
+// 4-wide accessors: lane l owns columns [128 i + 4 l, +4) of vector i, so a warp's shared-memory access is 32
+// consecutive 16-byte (fp32) / 8-byte (bf16) words — conflict-free — and its global stores are fully coalesced
+__device__ __forceinline__ void load4(const float* p, float* v) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float* v) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  v[0] = bf16_lo(t.x); v[1] = bf16_hi(t.x); v[2] = bf16_lo(t.y); v[3] = bf16_hi(t.y);
+}
+__device__ __forceinline__ void store4(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float* v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
+// 4 dropout keep-flags for elements [e0, e0+4), e0 a multiple of 4 (same generator as drop8)
+__device__ __forceinline__ void drop4(uint32_t e0, uint32_t seed_lo, uint32_t seed_hi, uint32_t thr16, float scale,
+                                      float* v) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint32_t h = drop_hash((e0 >> 1) + j, seed_lo, seed_hi);
+    v[2 * j] = ((h & 0xffffu) >= thr16) ? v[2 * j] * scale : 0.f;
+    v[2 * j + 1] = ((h >> 16) >= thr16) ? v[2 * j + 1] * scale : 0.f;
+  }
+}
+
+// NV = d / 128 vectors of 4 columns per lane (d a multiple of 128)
+template <typename XT, int NV>
+__global__ void __launch_bounds__(LNP_THREADS, 1)
+ln_fwd_pipe_kernel(const XT* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const int32_t* __restrict__ seqlen, long long S, __nv_bfloat16* __restrict__ y,
+                   float* __restrict__ y32, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows,
+                   int d, float eps, int stages) {
+  extern __shared__ __align__(128) uint8_t lnp_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t row_bytes = (uint32_t)d * sizeof(XT);
+  uint8_t* ring = lnp_smem + (size_t)warp * stages * row_bytes;
+  float* sgamma = reinterpret_cast<float*>(lnp_smem + (size_t)LNP_WARPS * stages * row_bytes);
+  float* sbeta = sgamma + d;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbeta + d) + warp * LNP_MAX_STAGES;
+  for (int c = threadIdx.x; c < d; c += LNP_THREADS) { sgamma[c] = gamma[c]; sbeta[c] = beta[c]; }
+  if (lane == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const long long warp0 = (long long)blockIdx.x * LNP_WARPS + warp;
+  const long long nwarps = (long long)gridDim.x * LNP_WARPS;
+  const long long n_my = warp0 < rows ? (rows - warp0 + nwarps - 1) / nwarps : 0;
+  auto issue = [&](long long k) {  // lane 0: request this warp's k-th row into ring slot k % stages
+    const int s = (int)(k % stages);
+    mbar_arrive_expect_tx(&bars[s], row_bytes);
+    bulk_load_1d(ring + (size_t)s * row_bytes, x + (warp0 + k * nwarps) * d, row_bytes, &bars[s]);
+  };
+  if (lane == 0)
+    for (long long k = 0; k < n_my && k < stages; ++k) issue(k);
+  // this lane's gamma / beta never change: keep them in registers (2 * 4 * NV)
+  float gm[NV][4], bt[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { load4(sgamma + i * 128 + lane * 4, gm[i]); load4(sbeta + i * 128 + lane * 4, bt[i]); }
+  const float inv_d = 1.0f / d;
+  for (long long k = 0; k < n_my; ++k) {
+    const long long row = warp0 + k * nwarps;
+    const int s = (int)(k % stages);
+    bool valid = true;
+    if (seqlen != nullptr) valid = (row % S) < seqlen[row / S];
+    mbar_wait(&bars[s], (uint32_t)((k / stages) & 1));
+    const XT* xr = reinterpret_cast<const XT*>(ring + (size_t)s * row_bytes);
+    float v[NV][4];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) load4(xr + i * 128 + lane * 4, v[i]);
+    __syncwarp();  // every lane has its vectors in registers: the slot can take the row after next
+    if (lane == 0 && k + stages < n_my) issue(k + stages);
+    float p4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains instead of one of 4 NV dependent adds
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p4[j] += v[i][j];
+    const float mean = warp_sum((p4[0] + p4[1]) + (p4[2] + p4[3])) * inv_d;
+    float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { v[i][j] -= mean; q4[j] = fmaf(v[i][j], v[i][j], q4[j]); }
+    const float rstd = rsqrtf(warp_sum((q4[0] + q4[1]) + (q4[2] + q4[3])) * inv_d + eps);
+    const float rs = valid ? rstd : 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = valid ? fmaf(v[i][j] * rs, gm[i][j], bt[i][j]) : 0.f;
+      store4(y + row * d + i * 128 + lane * 4, o);
+      if (y32 != nullptr) store4(y32 + row * d + i * 128 + lane * 4, o);
+    }
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  }
+}
+
 // =================================================================================================
 // LayerNorm backward.
 //   dy_eff = mask * dropout_dy(dy)                 (dropout_dy: a dropout that followed the LN)
@@ -143,6 +254,7 @@ struct LnBwdParams {
   const uint64_t* seed_mix;
   float* dgamma; float* dbeta; float* dbias;
   long long rows; int d;
+  float* col_scratch;  // optional [LN_PARTS_MAX][3][d]: per-CTA column partials of the fused row+column pass
 };
 
 // Pass 1 — one warp per row, no per-thread column accumulators (keeps registers low and occupancy high:
@@ -204,6 +316,258 @@ ln_bwd_dx_kernel(const LnBwdParams p) {
       }
     }
   }
+}
+
+// Fused pass — the row pass above PLUS the column sums (dgamma, dbeta, dbias) accumulated in registers while the row
+// is in flight, so dy / x / dx_drop are read once instead of twice (the fp32 residual stream doubled their size).
+// Every lane owns the same 8-column chunks of every row it visits; a CTA folds its warps through shared memory and
+// stores ONE partial per column into its slot of `col_scratch` (no atomics here: thousands of CTAs adding into
+// the same 2 304 addresses serialise in L2); ln_colpart_reduce_kernel adds the slots.
+constexpr int LNF_THREADS = 128;
+constexpr int LNF_WARPS = LNF_THREADS / 32;
+constexpr int LN_PARTS_MAX = 512;
+template <typename XT, typename DYT, typename DXT, int MAXC>
+__global__ void __launch_bounds__(LNF_THREADS, 3)
+ln_bwd_fused_kernel(const LnBwdParams p) {
+  __shared__ float sfold[LNF_WARPS][MAXC * 256];
+  const int d = p.d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp0 = (long long)blockIdx.x * LNF_WARPS + warp;
+  const long long nwarps = (long long)gridDim.x * LNF_WARPS;
+  const int nchunks = d >> 3;
+  const XT* x = reinterpret_cast<const XT*>(p.x);
+  const DYT* dy = reinterpret_cast<const DYT*>(p.dy);
+  DXT* dx = reinterpret_cast<DXT*>(p.dx);
+  uint32_t dy_lo = p.dy_seed_lo, dy_hi = p.dy_seed_hi, dx_lo = p.dx_seed_lo, dx_hi = p.dx_seed_hi;
+  if (p.dy_thr16 != 0) mix_seed(p.seed_mix, dy_lo, dy_hi);
+  if (p.dx_thr16 != 0) mix_seed(p.seed_mix, dx_lo, dx_hi);
+  float ag[MAXC][8], ab[MAXC][8], abias[MAXC][8];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ag[c][j] = 0.f; ab[c][j] = 0.f; abias[c][j] = 0.f; }
+  for (long long row = warp0; row < p.rows; row += nwarps) {
+    bool valid = true;
+    if (p.seqlen != nullptr) valid = (row % p.S) < p.seqlen[row / p.S];
+    const float mean = p.mean[row], rstd = p.rstd[row];
+    float xh[MAXC][8], g[MAXC][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
+        float xv[8], dv[8], gm[8];
+        load8(x + row * d + ch * 8, xv);
+        load8(dy + row * d + ch * 8, dv);
+        load8(p.gamma + ch * 8, gm);
+        if (p.dy_thr16 != 0)
+          drop8((uint32_t)row * (uint32_t)d + ch * 8, dy_lo, dy_hi, p.dy_thr16, p.dy_scale, dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[c][j] = (xv[j] - mean) * rstd;
+          const float de = valid ? dv[j] : 0.f;  // dy_eff
+          ag[c][j] = fmaf(de, xh[c][j], ag[c][j]);
+          ab[c][j] += de;
+          g[c][j] = de * gm[j];
+          s1 += g[c][j];
+          s2 = fmaf(g[c][j], xh[c][j], s2);
+        }
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunks) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[c][j] - s1 - xh[c][j] * s2);
+        store8(dx + row * d + ch * 8, o);
+        if (p.dx_drop != nullptr) {
+          if (p.dx_thr16 != 0)
+            drop8((uint32_t)row * (uint32_t)d + ch * 8, dx_lo, dx_hi, p.dx_thr16, p.dx_scale, o);
+          store8(p.dx_drop + row * d + ch * 8, o);
+        }
+        // bias gradient of the preceding linear: column sum of its output gradient, taken from the fp32 values
+#pragma unroll
+        for (int j = 0; j < 8; ++j) abias[c][j] += o[j];
+      }
+    }
+  }
+  // fold the CTA's warps, one accumulator kind at a time; partial slot layout [blockIdx.x][kind][d]
+  float* slot = p.col_scratch + (long long)blockIdx.x * 3 * d;
+#pragma unroll
+  for (int kind = 0; kind < 3; ++kind) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sfold[warp][(lane + 32 * c) * 8 + j] = kind == 0 ? ag[c][j] : (kind == 1 ? ab[c][j] : abias[c][j]);
+    __syncthreads();
+    for (int col = threadIdx.x; col < d; col += LNF_THREADS) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < LNF_WARPS; ++w2) sum += sfold[w2][col];
+      slot[kind * d + col] = sum;
+    }
+  }
+}
+
+// The same fused pass with the rows streamed through per-warp shared-memory rings by bulk copies (see
+// ln_fwd_pipe_kernel): the 72 column accumulators per lane leave no registers to prefetch the next row the classic
+// way, and with one row per warp in flight the register version reaches 68 % of the HBM peak.  One CTA of 12 warps
+// per SM => 148 partial slots instead of 444 for the reduction that follows.
+template <typename XT, typename DYT, typename DXT, int NV>
+__global__ void __launch_bounds__(LNP_THREADS, 1)
+ln_bwd_pipe_kernel(const LnBwdParams p, int stages) {
+  extern __shared__ __align__(128) uint8_t lnp_smem[];
+  const int d = p.d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t xb = (uint32_t)d * sizeof(XT), yb = (uint32_t)d * sizeof(DYT), stage_bytes = xb + yb;
+  uint8_t* ring = lnp_smem + (size_t)warp * stages * stage_bytes;
+  float* sgamma = reinterpret_cast<float*>(lnp_smem + (size_t)LNP_WARPS * stages * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sgamma + d) + warp * LNP_MAX_STAGES;
+  for (int c = threadIdx.x; c < d; c += LNP_THREADS) sgamma[c] = p.gamma[c];
+  if (lane == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const XT* x = reinterpret_cast<const XT*>(p.x);
+  const DYT* dy = reinterpret_cast<const DYT*>(p.dy);
+  DXT* dx = reinterpret_cast<DXT*>(p.dx);
+  const long long warp0 = (long long)blockIdx.x * LNP_WARPS + warp;
+  const long long nwarps = (long long)gridDim.x * LNP_WARPS;
+  const long long n_my = warp0 < p.rows ? (p.rows - warp0 + nwarps - 1) / nwarps : 0;
+  auto issue = [&](long long k) {
+    const int s = (int)(k % stages);
+    const long long row = warp0 + k * nwarps;
+    mbar_arrive_expect_tx(&bars[s], stage_bytes);
+    bulk_load_1d(ring + (size_t)s * stage_bytes, x + row * d, xb, &bars[s]);
+    bulk_load_1d(ring + (size_t)s * stage_bytes + xb, dy + row * d, yb, &bars[s]);
+  };
+  if (lane == 0)
+    for (long long k = 0; k < n_my && k < stages; ++k) issue(k);
+  uint32_t dy_lo = p.dy_seed_lo, dy_hi = p.dy_seed_hi, dx_lo = p.dx_seed_lo, dx_hi = p.dx_seed_hi;
+  if (p.dy_thr16 != 0) mix_seed(p.seed_mix, dy_lo, dy_hi);
+  if (p.dx_thr16 != 0) mix_seed(p.seed_mix, dx_lo, dx_hi);
+  const float inv_d = 1.0f / d;
+  float ag[NV][4], ab[NV][4], abias[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; abias[i][j] = 0.f; }
+  for (long long k = 0; k < n_my; ++k) {
+    const long long row = warp0 + k * nwarps;
+    const int s = (int)(k % stages);
+    bool valid = true;
+    if (p.seqlen != nullptr) valid = (row % p.S) < p.seqlen[row / p.S];
+    const float mean = p.mean[row], rstd = p.rstd[row];
+    mbar_wait(&bars[s], (uint32_t)((k / stages) & 1));
+    const XT* xr = reinterpret_cast<const XT*>(ring + (size_t)s * stage_bytes);
+    const DYT* dr = reinterpret_cast<const DYT*>(ring + (size_t)s * stage_bytes + xb);
+    float xh[NV][4], g[NV][4];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { load4(xr + i * 128 + lane * 4, xh[i]); load4(dr + i * 128 + lane * 4, g[i]); }
+    __syncwarp();  // the row is in registers: refill the slot
+    if (lane == 0 && k + stages < n_my) issue(k + stages);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    const float nmr = -mean * rstd;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float gm[4];
+      load4(sgamma + i * 128 + lane * 4, gm);
+      if (p.dy_thr16 != 0)
+        drop4((uint32_t)row * (uint32_t)d + i * 128 + lane * 4, dy_lo, dy_hi, p.dy_thr16, p.dy_scale, g[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xh[i][j] = fmaf(xh[i][j], rstd, nmr);
+        const float de = valid ? g[i][j] : 0.f;  // dy_eff
+        ag[i][j] = fmaf(de, xh[i][j], ag[i][j]);
+        ab[i][j] += de;
+        g[i][j] = de * gm[j];
+        s1[j] += g[i][j];
+        s2[j] = fmaf(g[i][j], xh[i][j], s2[j]);
+      }
+    }
+    const float m1 = warp_sum((s1[0] + s1[1]) + (s1[2] + s1[3])) * inv_d;
+    const float m2 = warp_sum((s2[0] + s2[1]) + (s2[2] + s2[3])) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = rstd * (g[i][j] - m1 - xh[i][j] * m2);
+      store4(dx + row * d + i * 128 + lane * 4, o);
+      if (p.dx_drop != nullptr) {
+        if (p.dx_thr16 != 0)
+          drop4((uint32_t)row * (uint32_t)d + i * 128 + lane * 4, dx_lo, dx_hi, p.dx_thr16, p.dx_scale, o);
+        store4(p.dx_drop + row * d + i * 128 + lane * 4, o);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) abias[i][j] += o[j];
+    }
+  }
+  // every bulk copy this CTA issued has been waited for: the rings are free to hold the cross-warp fold
+  float* sfold = reinterpret_cast<float*>(lnp_smem);  // [LNP_WARPS][d]
+  float* slot = p.col_scratch + (long long)blockIdx.x * 3 * d;
+#pragma unroll
+  for (int kind = 0; kind < 3; ++kind) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float* src = kind == 0 ? ag[i] : (kind == 1 ? ab[i] : abias[i]);
+      store4(sfold + warp * d + i * 128 + lane * 4, src);
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < d; col += LNP_THREADS) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < LNP_WARPS; ++w2) sum += sfold[w2 * d + col];
+      slot[kind * d + col] = sum;
+    }
+  }
+}
+
+// dgamma / dbeta / dbias += sum over the n_part slots of col_scratch.  grid (ceil(3d / 256), LNR_GROUPS): every thread
+// adds its share of the slots for one (kind, column) and issues one atomic (LNR_GROUPS-way contention per address).
+constexpr int LNR_GROUPS = 8;
+__global__ void __launch_bounds__(EW_THREADS)
+ln_colpart_reduce_kernel(const float* __restrict__ part, int n_part, int d, float* __restrict__ dgamma,
+                         float* __restrict__ dbeta, float* __restrict__ dbias) {
+  const int idx = blockIdx.x * EW_THREADS + threadIdx.x;  // kind * d + col
+  if (idx >= 3 * d) return;
+  const int kind = idx / d, col = idx - kind * d;
+  float* dst = kind == 0 ? dgamma : (kind == 1 ? dbeta : dbias);
+  if (dst == nullptr) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int s = blockIdx.y;
+  for (; s + 3 * LNR_GROUPS < n_part; s += 4 * LNR_GROUPS) {
+    a0 += part[(long long)s * 3 * d + idx];
+    a1 += part[(long long)(s + LNR_GROUPS) * 3 * d + idx];
+    a2 += part[(long long)(s + 2 * LNR_GROUPS) * 3 * d + idx];
+    a3 += part[(long long)(s + 3 * LNR_GROUPS) * 3 * d + idx];
+  }
+  for (; s < n_part; s += LNR_GROUPS) a0 += part[(long long)s * 3 * d + idx];
+  atomicAdd(dst + col, (a0 + a1) + (a2 + a3));
+}
+
+// M3P_LN_PIPE=0 falls back to the register-staged kernels (A/B measurements)
+static bool use_ln_pipe() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("M3P_LN_PIPE");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+static int ln_fused_grid(long long rows) {
+  long long need = (rows + LNF_WARPS - 1) / LNF_WARPS;
+  long long cap = (long long)sm_count() * 3;
+  if (cap > LN_PARTS_MAX) cap = LN_PARTS_MAX;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
 // Column-reduction geometry shared by the LayerNorm column pass and the bias-gradient column sums:
@@ -325,6 +689,52 @@ ln_bwd_cols_kernel(const LnBwdParams p, const BT* __restrict__ bias_src, int tx,
 
 template <typename XT, typename DYT, typename DXT>
 static int launch_ln_bwd(LnBwdParams p, cudaStream_t stream, int phases) {
+  if (p.col_scratch != nullptr && p.d <= 1024 && (p.dgamma || p.dbeta || p.dbias)) {
+    // fused row + column pass into per-CTA partials (phase 1), partial reduction (phase 2)
+    const uint32_t stage_bytes = (uint32_t)p.d * (sizeof(XT) + sizeof(DYT));
+    const uint32_t tail = (uint32_t)p.d * 4 + LNP_WARPS * LNP_MAX_STAGES * 8;
+    int stages = (int)((LNP_SMEM_BUDGET - tail) / (LNP_WARPS * stage_bytes));
+    if (stages > LNP_MAX_STAGES) stages = LNP_MAX_STAGES;
+    const bool pipe = use_ln_pipe() && stages >= 2 && p.rows >= 4096 && p.d % 128 == 0 &&
+                      (p.d == 256 || p.d == 512 || p.d == 768 || p.d == 1024);
+    if (pipe) {
+      const int pgrid = sm_count() < LN_PARTS_MAX ? sm_count() : LN_PARTS_MAX;
+      const size_t smem = (size_t)LNP_WARPS * stages * stage_bytes + tail;
+      if (phases & 1) {
+#define M3P_LN_BWD_PIPE(NV)                                                                               \
+  do {                                                                                                    \
+    auto kfn = ln_bwd_pipe_kernel<XT, DYT, DXT, NV>;                                                    \
+    M3P_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LNP_SMEM_BUDGET + 4096)); \
+    kfn<<<pgrid, LNP_THREADS, smem, stream>>>(p, stages);                                                 \
+  } while (0)
+        if (p.d == 256) M3P_LN_BWD_PIPE(2);
+        else if (p.d == 512) M3P_LN_BWD_PIPE(4);
+        else if (p.d == 768) M3P_LN_BWD_PIPE(6);
+        else M3P_LN_BWD_PIPE(8);
+#undef M3P_LN_BWD_PIPE
+        M3P_CUDA_OK(cudaGetLastError());
+      }
+      if (phases & 2) {
+        const dim3 rgrid((3 * p.d + EW_THREADS - 1) / EW_THREADS, LNR_GROUPS);
+        ln_colpart_reduce_kernel<<<rgrid, EW_THREADS, 0, stream>>>(p.col_scratch, pgrid, p.d, p.dgamma, p.dbeta, p.dbias);
+        M3P_CUDA_OK(cudaGetLastError());
+      }
+      return M3P_OK;
+    }
+    const int grid = ln_fused_grid(p.rows);
+    if (phases & 1) {
+      if (p.d <= 256) ln_bwd_fused_kernel<XT, DYT, DXT, 1><<<grid, LNF_THREADS, 0, stream>>>(p);
+      else if (p.d <= 768) ln_bwd_fused_kernel<XT, DYT, DXT, 3><<<grid, LNF_THREADS, 0, stream>>>(p);
+      else ln_bwd_fused_kernel<XT, DYT, DXT, 4><<<grid, LNF_THREADS, 0, stream>>>(p);
+      M3P_CUDA_OK(cudaGetLastError());
+    }
+    if (phases & 2) {
+      const dim3 rgrid((3 * p.d + EW_THREADS - 1) / EW_THREADS, LNR_GROUPS);
+      ln_colpart_reduce_kernel<<<rgrid, EW_THREADS, 0, stream>>>(p.col_scratch, grid, p.d, p.dgamma, p.dbeta, p.dbias);
+      M3P_CUDA_OK(cudaGetLastError());
+    }
+    return M3P_OK;
+  }
   if (phases & 1) {
     const int grid = ew_grid(p.rows);
     if (p.d <= 256) ln_bwd_dx_kernel<XT, DYT, DXT, 1><<<grid, EW_THREADS, 0, stream>>>(p);
@@ -749,11 +1159,32 @@ scatter_add_rows_f32_kernel(const float* __restrict__ src, const int64_t* __rest
 using namespace m3p;
 
 template <typename XT>
-static void launch_ln_fwd(const m3p_ln_fwd_args* a, cudaStream_t stream) {
-  const int grid = ew_grid(a->rows);
+static int launch_ln_fwd(const m3p_ln_fwd_args* a, cudaStream_t stream) {
   auto X = reinterpret_cast<const XT*>(a->x);
   auto Y = reinterpret_cast<__nv_bfloat16*>(a->y);
   const int d = (int)a->d;
+  if (use_ln_pipe() && a->rows >= 4096 && (d == 256 || d == 512 || d == 768 || d == 1024)) {
+    const uint32_t row_bytes = (uint32_t)d * sizeof(XT);
+    const uint32_t tail = (uint32_t)d * 8 + LNP_WARPS * LNP_MAX_STAGES * 8;
+    int stages = (int)((LNP_SMEM_BUDGET - tail) / (LNP_WARPS * row_bytes));
+    if (stages > LNP_MAX_STAGES) stages = LNP_MAX_STAGES;
+    const size_t smem = (size_t)LNP_WARPS * stages * row_bytes + tail;
+    const int pgrid = sm_count();
+#define M3P_LN_FWD_PIPE(NV)                                                                               \
+  do {                                                                                                    \
+    auto kfn = ln_fwd_pipe_kernel<XT, NV>;                                                              \
+    M3P_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LNP_SMEM_BUDGET + 4096)); \
+    kfn<<<pgrid, LNP_THREADS, smem, stream>>>(X, a->gamma, a->beta, a->seqlen, a->S, Y, a->y_f32, a->mean, a->rstd, \
+                                              a->rows, d, a->eps, stages);                                \
+  } while (0)
+    if (d == 256) M3P_LN_FWD_PIPE(2);
+    else if (d == 512) M3P_LN_FWD_PIPE(4);
+    else if (d == 768) M3P_LN_FWD_PIPE(6);
+    else M3P_LN_FWD_PIPE(8);
+#undef M3P_LN_FWD_PIPE
+    return M3P_OK;
+  }
+  const int grid = ew_grid(a->rows);
 #define M3P_LN_FWD(MAXC) ln_fwd_kernel<XT, MAXC><<<grid, EW_THREADS, 0, stream>>>( \
       X, a->gamma, a->beta, a->seqlen, a->S, Y, a->y_f32, a->mean, a->rstd, a->rows, d, a->eps)
   if (d <= 256) M3P_LN_FWD(1);
@@ -761,6 +1192,7 @@ static void launch_ln_fwd(const m3p_ln_fwd_args* a, cudaStream_t stream) {
   else if (d <= 1024) M3P_LN_FWD(4);
   else M3P_LN_FWD(8);
 #undef M3P_LN_FWD
+  return M3P_OK;
 }
 
 extern "C" int m3p_layernorm_fwd(const m3p_ln_fwd_args* a, m3p_stream_t stream_) {
@@ -769,8 +1201,8 @@ extern "C" int m3p_layernorm_fwd(const m3p_ln_fwd_args* a, m3p_stream_t stream_)
   M3P_REQUIRE(a->rows > 0 && a->d > 0 && a->d % 8 == 0 && a->d <= 2048,
               "m3p_layernorm_fwd: d=%lld must be a multiple of 8, <= 2048", (long long)a->d);
   M3P_REQUIRE(a->seqlen == nullptr || a->S > 0, "m3p_layernorm_fwd: S must be > 0 with a row mask");
-  if (a->x_f32) launch_ln_fwd<float>(a, stream);
-  else launch_ln_fwd<__nv_bfloat16>(a, stream);
+  const int rc = a->x_f32 ? launch_ln_fwd<float>(a, stream) : launch_ln_fwd<__nv_bfloat16>(a, stream);
+  if (rc) return rc;
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }
@@ -797,6 +1229,7 @@ static int layernorm_bwd_impl(const m3p_ln_bwd_args* a, m3p_stream_t stream_, in
   p.seed_mix = seed_mix_ptr();
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dbias = a->dbias;
   p.rows = a->rows; p.d = (int)a->d;
+  p.col_scratch = a->col_scratch;
   const int key = (a->x_f32 ? 4 : 0) | (a->dy_f32 ? 2 : 0) | (a->dx_f32 ? 1 : 0);
   switch (key) {
     case 0: return launch_ln_bwd<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(p, stream, phases);

@@ -63,6 +63,7 @@ class LnBwdArgs(ctypes.Structure):
         ("dgamma", c_void_p), ("dbeta", c_void_p), ("dbias", c_void_p),
         ("rows", c_int64), ("d", c_int64),
         ("x_f32", c_int32), ("dy_f32", c_int32), ("dx_f32", c_int32),
+        ("col_scratch", c_void_p),
     ]
 
 

@@ -153,7 +153,7 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps, seqlen=None, S=0, y32=None
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, *, seqlen=None, S=0, dx_drop=None, dx_drop_p=0.0, dx_seed=0,
-                  dy_drop_p=0.0, dy_seed=0, dgamma=None, dbeta=None, dbias=None, phase="both"):
+                  dy_drop_p=0.0, dy_seed=0, dgamma=None, dbeta=None, dbias=None, phase="both", col_scratch=None):
     """phase: "both" (row pass then column pass), "rows" (dx / dx_drop only) or "cols" (dgamma / dbeta / dbias
     only, after the row pass of the same arguments has been enqueued)."""
     a = L.LnBwdArgs()
@@ -163,6 +163,9 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, *, seqlen=None, S=0, dx_drop=Non
     a.dx_drop_p, a.dx_seed, a.dy_drop_p, a.dy_seed = dx_drop_p, dx_seed, dy_drop_p, dy_seed
     a.dgamma, a.dbeta, a.dbias = _p(dgamma), _p(dbeta), _p(dbias)
     a.rows, a.d = x.shape
+    a.col_scratch = _p(col_scratch)
+    if col_scratch is not None:
+        assert col_scratch.dtype == torch.float32 and col_scratch.numel() >= 512 * 3 * x.shape[1]
     a.x_f32 = int(x.dtype == torch.float32)
     a.dy_f32 = int(dy.dtype == torch.float32)
     a.dx_f32 = int(dx.dtype == torch.float32)

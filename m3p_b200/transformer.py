@@ -708,8 +708,11 @@ class TransformerModel(nn.Module):
             w, gr, s = self._layer_views(i), self._layer_grads(i), st["layers"][i]
             # layer_norm2 (+ row mask) and the FFN dropout           (:956-958, :226)
             dx2, dx2d = e(M, d, dt=_F32), e(M, d)
+            # col_scratch: the row pass also accumulates the column sums into per-CTA partials (one read of dh / x2);
+            # the "cols" call on the side stream only adds the partials into the parameter gradients
+            scr2, scr1 = e(512 * 3 * d, dt=_F32), e(512 * 3 * d, dt=_F32)
             ln2 = dict(seqlen=seqlen, S=S, dx_drop=dx2d, dx_drop_p=p_drop, dx_seed=s["s2"], dgamma=gr["g2"],
-                       dbeta=gr["b2"], dbias=gr["bb2"])
+                       dbeta=gr["b2"], dbias=gr["bb2"], col_scratch=scr2)
             ops.layernorm_bwd(dh, s["x2"], s["mean2"], s["rstd2"], w["g2"], dx2, phase="rows", **ln2)
             dx2d_ = dx2d
             sq.fork()
@@ -725,7 +728,8 @@ class TransformerModel(nn.Module):
             ops.dgrad(du, w["w1"], dh1, epi=L.M3P_EPI_DROP_RES, aux=dx2, out_f32=True)
             # layer_norm1 and the attention-output dropout              (:951-953)
             dx1, dx1d = e(M, d, dt=_F32), e(M, d)
-            ln1 = dict(dx_drop=dx1d, dx_drop_p=p_drop, dx_seed=s["s1"], dgamma=gr["g1"], dbeta=gr["b1"], dbias=gr["bo"])
+            ln1 = dict(dx_drop=dx1d, dx_drop_p=p_drop, dx_seed=s["s1"], dgamma=gr["g1"], dbeta=gr["b1"], dbias=gr["bo"],
+                       col_scratch=scr1)
             ops.layernorm_bwd(dh1, s["x1"], s["mean1"], s["rstd1"], w["g1"], dx1, phase="rows", **ln1)
             dx1d_ = dx1d
             sq.fork()
@@ -742,7 +746,7 @@ class TransformerModel(nn.Module):
             dhp = e(M, d, dt=_F32)
             ops.dgrad(dqkv, w["wqkv"], dhp, epi=L.M3P_EPI_DROP_RES, aux=dx1, out_f32=True)
             # the side stream may still be reading these: keep them alive until the join one layer later
-            sq.close("layer%d" % i, self._segments["layer%d" % i], (dh, s, dx2, dx2d, du, dh1, dx1, dx1d, dqkv))
+            sq.close("layer%d" % i, self._segments["layer%d" % i], (dh, s, dx2, dx2d, du, dh1, dx1, dx1d, dqkv, scr1, scr2))
             if self._bwd_trace is not None:  # tests only: every intermediate of this layer's backward, for stage parity
                 self._bwd_trace.append(dict(layer=i, stash=s, dh=dh, dx2=dx2, dx2d=dx2d, du=du, dh1=dh1, dx1=dx1,
                                             dx1d=dx1d, dctx=dctx, dqkv=dqkv, dhp=dhp))
