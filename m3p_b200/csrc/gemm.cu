@@ -272,6 +272,11 @@ __device__ __forceinline__ void epilogue_chunk_direct(const GemmKernelParams& p,
 // CTA2 = true: the kernel runs as clusters of two CTAs issuing cta_group::2 MMAs on a 256 x BN tile;
 // each CTA stages its own 128 rows of A and its own BN/2 rows of B (32 KB / k-block instead of 48 KB:
 // the 128 x 256 single-CTA tile is bound by the ~64 B/clk L2 -> SM path at ~2/3 of tensor peak).
+#ifndef M3P_AUX_RING
+#define M3P_AUX_RING 3
+#endif
+constexpr int AUX_RING_MAX = 6;
+
 template <int BN, bool CTA2, int EPI, bool OUT_F32>
 struct GemmCfg {
   static constexpr int BN_LOAD = CTA2 ? BN / 2 : BN;  // B rows this CTA stages per k-block
@@ -285,10 +290,18 @@ struct GemmCfg {
   // result and TMA-STORE it (ring of 3); the others only store (ring of 2).
   static constexpr bool F32R = f32_ring<EPI, OUT_F32>();
   static constexpr int N_OUT = OUT_F32 ? (F32R ? 1 : 0) : (EPI == M3P_EPI_GELU ? 2 : 1);
-  static constexpr int RING = epi_has_aux<EPI>() ? 3 : 2;
+  // Ring depth of the aux epilogues: after staging group gg a warp may only refill a slot whose TMA store has
+  // finished READING it.  With RING = 3 that is the store issued one group earlier, so lane 0 sat in wait_group.read
+  // for most of a store latency at every group and the refill ran just two groups ahead of its use — the epilogue of
+  // the residual GEMMs was latency-bound (25 k cycles per 256 x 256 tile against a 6 k-cycle K = 768 main loop).
+  // AUX_WAIT = 2 waits for the store issued TWO groups earlier (done long ago) and the deeper ring keeps
+  // RING - AUX_WAIT aux tiles in flight per warp.
+  static constexpr int RING = epi_has_aux<EPI>() ? M3P_AUX_RING : 2;
+  static constexpr int AUX_WAIT = RING >= 4 ? 2 : 1;
+  static constexpr int AUX_LEAD = RING - AUX_WAIT;
   static constexpr uint32_t WARP_STG = N_OUT * RING * STG_TILE;
   static constexpr uint32_t STG_BYTES = EPI_WARPS * WARP_STG;
-  static constexpr uint32_t BAR_BYTES = 512;
+  static constexpr uint32_t BAR_BYTES = 640;
   static constexpr uint32_t BUDGET = 220 * 1024;
   static constexpr int STAGES_FIT = (BUDGET - STG_BYTES - BIAS_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
@@ -314,8 +327,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* aux_bar = tmem_empty + 2;  // [EPI_WARPS][3]: aux tile of a ring slot has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS * 3);
+  uint64_t* aux_bar = tmem_empty + 2;  // [EPI_WARPS][AUX_RING_MAX]: aux tile of a ring slot has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS * AUX_RING_MAX);
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -343,7 +356,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], EPI_WARPS * NCTA);  // one arrival per epilogue warp of every CTA of the pair
     }
-    for (int i = 0; i < EPI_WARPS * 3; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < EPI_WARPS * AUX_RING_MAX; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -466,7 +479,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int cbase = half * (BN / 2);
     float* sbias = bias_smem + ew * (BN / 2);
     uint8_t* ring = stg_smem + ew * Cfg::WARP_STG;  // slot b, output o at ring + (b * N_OUT + o) * STG_TILE
-    uint64_t* my_aux_bar = aux_bar + ew * 3;
+    uint64_t* my_aux_bar = aux_bar + ew * AUX_RING_MAX;
     const bool use_tma = (!OUT_F32 || F32R) && p.tma_store;
     uint32_t seed_lo = p.seed_lo, seed_hi = p.seed_hi;
     if constexpr (EPI == M3P_EPI_DROP_RES) mix_seed(p.seed_mix, seed_lo, seed_hi);
@@ -496,7 +509,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (++ax_g == NG) { ax_g = 0; ax_u += unit_stride; ax_decode(); }
     };
     if constexpr (HAS_AUX) {
-      if (use_tma && lane == 0) { ax_decode(); issue_aux(); issue_aux(); }
+      if (use_tma && lane == 0) {
+        ax_decode();
+#pragma unroll
+        for (int i = 0; i < Cfg::AUX_LEAD; ++i) issue_aux();
+      }
     }
     uint32_t aux_phase = 0;  // bit b: parity the next wait on ring slot b expects
     int gg = 0;
@@ -599,7 +616,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
             tma_store_commit();  // one bulk group per staging group, valid or not: keeps the wait counts uniform
             if constexpr (HAS_AUX) {
-              tma_store_wait_read<1>();  // every store but the one just issued has been read: slot (gg + 2) % 3 is free
+              // all stores but the AUX_WAIT most recent have been read: slot (gg - AUX_WAIT + 1) % RING is free and
+              // takes the aux tile of group gg + AUX_LEAD
+              tma_store_wait_read<Cfg::AUX_WAIT>();
               issue_aux();
             }
           }
