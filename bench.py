@@ -104,15 +104,109 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+REF_STAGE = os.path.join(ROOT, "baseline", "_ref", "M3P")  # staged by __graft_entry__.build() (git-ignored)
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REF_STAGE, "src", "model", "transformer.py"))
+
+
+def _reference_model(device):
+    """The UNMODIFIED reference class (microsoft/M3P src/model/transformer.py, staged under baseline/_ref/ by
+    build()), constructed as model/__init__.py:93 does, M3P-base shape, fp32."""
+    import torch
+    if REF_STAGE not in sys.path:
+        sys.path.insert(0, REF_STAGE)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from src.model.transformer import TransformerModel as RefModel
+    torch.manual_seed(0)
+    return RefModel(namespace(CFG, 0.0), is_encoder=True, with_output=True, is_crossModal=True).to(device).train()
+
+
+def _reference_step(model, batch, heads):
+    """pretrain_under_step's forward + loss assembly (xtrainer.py:2281-2375) on the reference class + backward."""
+    import torch.nn.functional as F
+    R = batch["x_img"].shape[0]
+    enc = model("jointfwd", x=batch["x"], lengths=batch["lengths"], x_img=batch["x_img"], lengths_img=batch["lengths_img"],
+                causal=False, langs=None, image_loc=batch["image_loc"], refine_image=False)
+    total = 0.0
+    if "mlm" in heads:
+        total = total + model("predict", tensor=enc[R:], pred_mask=batch["pred_mask_text"], y=batch["y_text"], get_scores=False)[1]
+    if "mrm" in heads:
+        total = total + model("predict", tensor=enc[:R].transpose(0, 1), pred_mask=None, y=batch["obj_labels"].view(-1),
+                              get_scores=False, is_obj=True)[1]
+    if "mrfr" in heads:
+        reg = model("predict", tensor=enc[:R].transpose(0, 1), is_mrfr=True).reshape(-1, 2048)
+        sel = batch["obj_labels"].reshape(-1) != -1
+        total = total + F.mse_loss(reg[sel], batch["ori_feats"].reshape(-1, 2048)[sel])
+    if "rel" in heads:
+        sc = model("predict", tensor=enc.transpose(0, 1), is_relation=True)
+        n = CFG["sample_n"]
+        total = total + F.cross_entropy(sc.view(-1, n), batch["pos_labels"]) + F.binary_cross_entropy_with_logits(
+            sc.view(-1), F.one_hot(batch["pos_labels"], n).float().view(-1))
+    model.zero_grad(set_to_none=True)
+    total.backward()
+    return total
+
+
 def cpu_reference_pairs_per_s(heads, steps, warmup, threads=None):
-    """The reference algorithm on host cores: oracle/m3p_oracle.py (fp32 PyTorch restatement of
-    transformer.py + xtrainer.py loss assembly), full M3P-base weights, a B = 4 sample of the batch."""
+    """The reference's own CPU path on the box's host cores: the unmodified reference class when it has been staged
+    (kind "reference"), else the oracle port of the same algorithm (kind "port").  Full M3P-base weights, fp32, a
+    B = CPU_SAMPLE_PAIRS sample of the batch.  Returns (pairs/s, threads, s/step, kind)."""
+    import torch
+    from m3p_b200.train_step import synthetic_batch
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    B = CPU_SAMPLE_PAIRS
+    if reference_available():
+        model = _reference_model("cpu")
+        batch = synthetic_batch(B, CFG["T"], CFG["R"], CFG["n_words"], sample_n=CFG["sample_n"], seed=1234)
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            _reference_step(model, batch, heads)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        return B * len(times) / sum(times), threads, sum(times) / len(times), "reference"
+    return _cpu_port_pairs_per_s(heads, steps, warmup, threads) + ("port",)
+
+
+def reference_on_b200(heads, B=16, steps=3):
+    """Context line: the same unmodified reference class in eager PyTorch ON THE B200 (fp32, and under
+    torch.autocast(bfloat16)) — what a user of the reference gets on this GPU without this library."""
+    import torch
+    from m3p_b200.train_step import synthetic_batch
+    if not reference_available():
+        return None
+    out = {"pairs_per_step": B, "kind": "unmodified reference class, eager PyTorch, dropout 0"}
+    model = _reference_model("cuda")
+    batch = synthetic_batch(B, CFG["T"], CFG["R"], CFG["n_words"], sample_n=CFG["sample_n"], seed=1234, device="cuda")
+    for name, ac in (("fp32", False), ("autocast_bf16", True)):
+        ts = []
+        for it in range(steps + 2):
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                _reference_step(model, batch, heads)
+            t1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                ts.append(t0.elapsed_time(t1))
+        out[name + "_pairs_per_s"] = B * len(ts) / (sum(ts) * 1e-3)
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def _cpu_port_pairs_per_s(heads, steps, warmup, threads):
+    """Fallback when the reference has not been staged: oracle/m3p_oracle.py (fp32 PyTorch restatement of
+    transformer.py + xtrainer.py loss assembly)."""
     import torch
     from m3p_b200.transformer import TransformerModel
     from m3p_b200.train_step import synthetic_batch
     from oracle import m3p_oracle as O
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
     torch.manual_seed(0)
     model = TransformerModel(namespace(CFG, 0.0), is_encoder=True, with_output=True, is_crossModal=True)
     sd = {k: v.detach() for k, v in model.state_dict().items()}
@@ -142,14 +236,15 @@ def run_reference(args):
     if rank != 0:
         return
     heads = HEADS[args.heads]
-    v, threads, spt = cpu_reference_pairs_per_s(heads, args.steps, args.warmup)
-    sample = "%d pairs/step x %d steps, M3P-base fp32, oracle port on %d host threads" % (CPU_SAMPLE_PAIRS, args.steps, threads)
+    v, threads, spt, kind = cpu_reference_pairs_per_s(heads, args.steps, args.warmup)
+    sample = "%d pairs/step x %d steps, M3P-base fp32, %s on %d host threads" % (
+        CPU_SAMPLE_PAIRS, args.steps, "unmodified reference class (baseline/_ref)" if kind == "reference" else "oracle port", threads)
     print(json.dumps({
         "impl": "reference", "metric": "image-text pairs/sec fwd+bwd, M3P-base 228-tok seq", "value": v, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.heads), "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 
@@ -182,6 +277,42 @@ def time_dominant_kernel(torch, ops, L):
             times.append(t0.elapsed_time(t1))
     ms = statistics.median(times)
     return 2.0 * m * n * k / (ms * 1e-3) / 1e12, ms
+
+
+def dominant_kernel_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r02_ncu_dominant.json, written by tools/ncu_dominant.py from the .ncu-rep);
+    None when no capture has been committed."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_dominant.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    return d.get("dram_bytes_read", 0) + d.get("dram_bytes_write", 0), d
+
+
+def time_optimizer(torch, model):
+    """the fused clip + Adam step over the model's flat buffers, timed alone (CUDA events) against the
+    HBM roofline: sumsq reads 4 B/param; the Adam pass reads p, g, m, v and writes p, m, v, g (zeroed) in fp32 plus
+    the bf16 operand copy = 34 B/param."""
+    from m3p_b200 import optim
+    opt = optim.get_optimizer([p for p in model.parameters() if p.requires_grad], "adam,lr=0.00001", clip_grad_norm=5.0)
+    n_params = model._flat_numel + model._emb.numel()
+    ts = []
+    for it in range(7):
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        opt.step()
+        t1.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            ts.append(t0.elapsed_time(t1))
+    ms = statistics.median(ts)
+    nbytes = n_params * 38.0
+    pk = peaks()
+    return {"ms": ms, "params": n_params, "bytes_per_param": 38, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
+            "peak_gbs": pk["hbm"], "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"],
+            "note": "clip_grad_norm (m3p_sumsq_f32, 4 B/param) + m3p_adam_step (34 B/param) on the flat fp32 buffers, "
+                    "timed alone; not part of the fwd+bwd metric"}
 
 
 def main():
@@ -311,6 +442,7 @@ def main():
     out = None
     if rank == 0:
         dom_tf, dom_ms = time_dominant_kernel(torch, ops, L)
+        dom_traffic, dom_src = dominant_kernel_traffic()
         out = {
             "metric": "image-text pairs/sec fwd+bwd, M3P-%s 228-tok seq" % args.model, "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -328,27 +460,32 @@ def main():
             "gpu_launches": (graphed.launches_per_step * args.steps) if graphed is not None else launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["sustained"], "traffic": None,
+                         "frac": achieved / pk["sustained"], "traffic": dom_traffic,
                          "scope": "whole fwd+bwd step per GPU: pairs/s x %.3f GFLOP/pair (BASELINE.md §3) over the "
                                   "sustained cuBLAS bf16 peak, %s" % (gf, pk["source"]),
                          "dominant_kernel": {"name": "gemm_kernel<256, GELU> FFN lin1 14592x3072x768", "ms": dom_ms,
                                              "achieved": dom_tf, "peak": pk["burst"], "frac": dom_tf / pk["burst"],
                                              "note": "timed alone, L2 flushed, vs burst peak",
-                                             "traffic": 152.4e6, "traffic_note": "dram__bytes_read+write per launch "
-                                             "(ncu --set full, profiles/r01_ncu_full_kernels.txt id 6: 27.3 MB read + "
-                                             "125.1 MB written; algorithmic 22.4 MB A + 4.7 MB W + 2 x 89.7 MB outputs, "
-                                             "part of which is still in L2 when the kernel ends)"}},
+                                             "traffic": dom_traffic,
+                                             "algorithmic_bytes": 14592 * 768 * 2 + 3072 * 768 * 2 + 2 * 14592 * 3072 * 2,
+                                             "traffic_note": "dram__bytes_read + dram__bytes_write of this kernel per "
+                                             "launch from the committed ncu --set full capture (%s); `roofline.traffic` "
+                                             "repeats it (the step itself is tensor-bound: bytes are not its roofline)"
+                                             % (dom_src.get("source") if dom_src else "no capture committed")}},
         }
     if world > 1:
         dist.barrier()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            del model
+            out["optimizer"] = time_optimizer(torch, model)
+            out["reference_on_b200"] = reference_on_b200(heads)
+            del model, graphed
             torch.cuda.empty_cache()
-            v, threads, _ = cpu_reference_pairs_per_s(heads, 3, 1)
-            out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+            v, threads, _, kind = cpu_reference_pairs_per_s(heads, 3, 1)
+            out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind,
                                    "sample": "%d pairs/step x 3 steps after 1 warm-up, same M3P-base weights shape and batch "
-                                             "generator, fp32 oracle port (oracle/m3p_oracle.py)" % CPU_SAMPLE_PAIRS}
+                                             "generator, fp32, %s" % (CPU_SAMPLE_PAIRS, "unmodified reference class "
+                                             "(baseline/_ref/M3P)" if kind == "reference" else "oracle port (oracle/m3p_oracle.py)")}
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out), flush=True)
