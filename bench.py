@@ -353,7 +353,8 @@ def main():
     B = args.batch
     torch.manual_seed(0)
     model = TransformerModel(namespace(CFG), is_encoder=True, with_output=True, is_crossModal=True).cuda().train()
-    reducer = GradReducer(model, overlap=os.environ.get("M3P_DDP_OVERLAP", "1") != "0")
+    reduce_dtype = None if os.environ.get("M3P_DDP_FP32", "0") == "1" else torch.bfloat16
+    reducer = GradReducer(model, overlap=os.environ.get("M3P_DDP_OVERLAP", "1") != "0", reduce_dtype=reduce_dtype)
     host = synthetic_batch(B, CFG["T"], CFG["R"], CFG["n_words"], sample_n=CFG["sample_n"], seed=1234 + rank)
     host = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
@@ -449,6 +450,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args.heads), "global_batch": B * world, "seq_len": CFG["T"] + CFG["R"],
                        "parallelism": "dp%d" % world, "dropout": CFG["dropout"], "vocab": CFG["n_words"],
+                       "grad_allreduce": None if world == 1 else ("bf16 slices on a comm stream inside backward + bf16 embedding rows"
+                                                                    if reduce_dtype is not None else "fp32"),
                        "launch": "CUDA graph replay (one capture of zero_grad+fwd+loss+bwd%s)" % (" + NCCL gradient exchange" if world > 1 else "") if graphed is not None
                        else "per-kernel launches from Python",
                        "l2": "per-step working set (0.18 GB bf16 weights + >4 GB activations) >> 126 MB L2; no flush needed",

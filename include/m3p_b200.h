@@ -221,6 +221,9 @@ M3P_API int m3p_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows,
 
 /* out = bf16(scale * in): refreshes the bf16 tensor-core copies of the fp32 master parameters. */
 M3P_API int m3p_cast_f32_bf16(const float* in, void* out, int64_t n, float scale, m3p_stream_t stream);
+/* out = scale * float(in): a bf16 buffer back into an fp32 one (the data-parallel gradient exchange reduces bf16
+ * copies of the flat gradient slices — Apex DDP all-reduces the AMP half-precision gradients, xtrainer.py:77-83). */
+M3P_API int m3p_cast_bf16_f32(const void* in, float* out, int64_t n, float scale, m3p_stream_t stream);
 /* out[i] = bf16(sum_{s < n_slabs} in[s * slab_stride + i]), slabs added in index order (deterministic reduction
  * of the split-K partials written with m3p_gemm_args.split_stride; d rows of the MLM head, transformer.py:104-117). */
 M3P_API int m3p_sum_slabs_bf16(const float* in, int64_t n_slabs, int64_t slab_stride, void* out, int64_t n,
@@ -279,6 +282,9 @@ M3P_API int m3p_gather_rows_f32(const float* table, const int64_t* idx, float* d
 /* dst[idx[i]][:] += src[i][:] (fp32, atomic), rows with idx == skip_index skipped. */
 M3P_API int m3p_scatter_add_rows_f32(const float* src, const int64_t* idx, int64_t skip_index, float* dst, int64_t n,
                                      int64_t d, m3p_stream_t stream);
+/* the same with bf16 source rows (all-gathered embedding-gradient rows of the data-parallel exchange). */
+M3P_API int m3p_scatter_add_rows_bf16(const void* src, const int64_t* idx, int64_t skip_index, float* dst, int64_t n,
+                                      int64_t d, m3p_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Embedding stage of jointfwd / fwd / crossfwd (transformer.py:897-943, 820-831, 1044-1062).

@@ -817,6 +817,18 @@ cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ o
     store8(out + i * 8, v);
   }
 }
+// out = scale * float(in): the way back from a bf16 gradient all-reduce into the fp32 gradient buffer
+__global__ void __launch_bounds__(EW_THREADS)
+cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n8, float scale) {
+  for (long long i = (long long)blockIdx.x * EW_THREADS + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * EW_THREADS) {
+    float v[8];
+    load8(in + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= scale;
+    store8(out + i * 8, v);
+  }
+}
 // out = bf16(sum_s in[s * stride + i]), slabs added in index order: the deterministic reduction of split-K partials
 // (m3p_gemm_args.split_stride) — no atomics, so a bf16 result cannot flip with the arrival order of the partial sums
 __global__ void __launch_bounds__(EW_THREADS)
@@ -1134,6 +1146,25 @@ gather_rows_f32_kernel(const float* __restrict__ table, const int64_t* __restric
   }
 }
 
+// same with bf16 source rows (the all-gathered embedding-gradient rows of the data-parallel exchange)
+__global__ void __launch_bounds__(EW_THREADS)
+scatter_add_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int64_t* __restrict__ idx, long long skip_index,
+                             float* __restrict__ dst, long long n, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * EW_WARPS;
+  for (long long i = warp0; i < n; i += nwarps) {
+    const long long r = idx[i];
+    if (r == skip_index) continue;
+    for (int c = lane; c < (d >> 3); c += 32) {
+      float v[8];
+      load8(src + i * d + c * 8, v);
+      atomicAdd(reinterpret_cast<float4*>(dst + r * d + c * 8), make_float4(v[0], v[1], v[2], v[3]));
+      atomicAdd(reinterpret_cast<float4*>(dst + r * d + c * 8 + 4), make_float4(v[4], v[5], v[6], v[7]));
+    }
+  }
+}
+
 // bf16 -> fp32 elementwise add into (embedding-style) fp32 rows:  dst[idx[i]][:] += src[i][:]
 __global__ void __launch_bounds__(EW_THREADS)
 scatter_add_rows_f32_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, long long skip_index,
@@ -1275,6 +1306,18 @@ extern "C" int m3p_cast_f32_bf16(const float* in, void* out, int64_t n, float sc
   long long g = (n8 + EW_THREADS - 1) / EW_THREADS;
   const long long cap = (long long)sm_count() * 16;
   cast_f32_bf16_kernel<<<(int)(g < cap ? g : cap), EW_THREADS, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n8, scale);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_cast_bf16_f32(const void* in, float* out, int64_t n, float scale, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(in && out, "m3p_cast_bf16_f32: null pointer");
+  M3P_REQUIRE(n > 0 && n % 8 == 0, "m3p_cast_bf16_f32: n must be a positive multiple of 8");
+  const long long n8 = n / 8;
+  long long g = (n8 + EW_THREADS - 1) / EW_THREADS;
+  const long long cap = (long long)sm_count() * 16;
+  cast_bf16_f32_kernel<<<(int)(g < cap ? g : cap), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, n8, scale);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }
@@ -1430,6 +1473,16 @@ extern "C" int m3p_gather_rows_f32(const float* table, const int64_t* idx, float
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   M3P_REQUIRE(table && idx && dst && n > 0 && d > 0 && d % 4 == 0, "m3p_gather_rows_f32: bad arguments");
   gather_rows_f32_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(table, idx, dst, n, (int)d);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_scatter_add_rows_bf16(const void* src, const int64_t* idx, int64_t skip_index, float* dst, int64_t n,
+                                         int64_t d, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(src && idx && dst && n > 0 && d > 0 && d % 8 == 0, "m3p_scatter_add_rows_bf16: bad arguments");
+  scatter_add_rows_bf16_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), idx,
+                                                                      skip_index, dst, n, (int)d);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }

@@ -16,10 +16,20 @@ import torch.distributed as dist
 
 
 class GradReducer:
-    def __init__(self, model, group=None, overlap=True):
+    """reduce_dtype=torch.bfloat16: every dense slice is cast to a persistent bf16 staging buffer, all-reduced (AVG)
+    and cast back into the fp32 gradient buffer, all on a dedicated communication stream — half the NVLink bytes and
+    half the time NCCL's CTAs compete with the persistent GEMMs of the backward (Apex DDP, the reference's
+    wrapper, all-reduces the half-precision AMP gradients the same way); the row-sparse embedding exchange sends
+    bf16 rows.  None keeps the exchange in fp32 (bit-comparable with a single-process run, tools/check_ddp.py)."""
+
+    def __init__(self, model, group=None, overlap=True, reduce_dtype=None):
         self.model = model
         self.group = group
         self.overlap = overlap
+        self.reduce_dtype = reduce_dtype
+        self._stage16 = {}   # (data_ptr, numel) of an fp32 slice -> persistent bf16 staging buffer
+        self._comm = None    # communication stream of the bf16 path
+        self._comm_pending = False
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._works = []
         self._done = set()
@@ -41,7 +51,36 @@ class GradReducer:
         delay_allreduce does the same: one all-reduce when the last backward ends.)"""
         return _NoSync(self)
 
+    def _allreduce_bf16(self, buf):
+        from . import ops
+        n = buf.numel()
+        key = (buf.data_ptr(), n)
+        if key not in self._stage16:
+            self._stage16[key] = torch.empty(n, dtype=torch.bfloat16, device=buf.device)
+        tmp = self._stage16[key]
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=buf.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._comm.wait_event(ev)                      # the slice is final on the compute stream
+        with torch.cuda.stream(self._comm), ops.on_stream(self._comm):
+            flat = buf.reshape(-1)
+            ops.cast_f32_bf16(flat, tmp, n, 1.0 if self._avg else 1.0 / self.world)
+            dist.all_reduce(tmp, op=dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM, group=self.group)
+            ops.cast_bf16_f32(tmp, flat, n)
+        self._comm_pending = True
+
+    def _join_comm(self):
+        if self._comm_pending:
+            ev = torch.cuda.Event()
+            ev.record(self._comm)
+            torch.cuda.current_stream().wait_event(ev)
+            self._comm_pending = False
+
     def _allreduce(self, buf):
+        if self.reduce_dtype == torch.bfloat16 and buf.is_cuda and buf.dtype == torch.float32 and buf.numel() % 8 == 0 \
+                and buf.is_contiguous():
+            return self._allreduce_bf16(buf)
         if self._avg:
             self._works.append(dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
         else:
@@ -78,11 +117,14 @@ class GradReducer:
         rows = g.index_select(0, ids) / (cnt.index_select(0, ids) * self.world).unsqueeze(1)
         # persistent receive buffers: the NEXT step's zero_grad clears the rows listed in all_ids, so under CUDA-graph
         # replay (and across eager steps) that tensor must stay where it is
-        key = (self.world * ids.numel(), g.shape[1], g.dtype, ids.device)
+        rdt = self.reduce_dtype if (self.reduce_dtype is not None and g.is_cuda) else g.dtype
+        key = (self.world * ids.numel(), g.shape[1], rdt, ids.device)
         if key not in self._gather:
             self._gather[key] = (torch.empty(key[0], dtype=ids.dtype, device=ids.device),
-                                 torch.empty(key[0], key[1], dtype=g.dtype, device=g.device))
+                                 torch.empty(key[0], key[1], dtype=rdt, device=g.device))
         all_ids, all_rows = self._gather[key]
+        if all_rows.dtype != rows.dtype:
+            rows = rows.to(all_rows.dtype)
         dist.all_gather_into_tensor(all_ids, ids, group=self.group)
         dist.all_gather_into_tensor(all_rows, rows, group=self.group)
         g.index_fill_(0, ids, 0.0)
@@ -108,15 +150,19 @@ class GradReducer:
         ids = torch.cat([x.t().reshape(-1) for x, _ in deferred])                  # batch-major, like the rows
         rows = torch.cat([gp.reshape(-1, g.shape[1]) for _, gp in deferred])
         rows = rows * ((ids != m.pad_index).to(rows.dtype) / self.world).unsqueeze(1)  # padding_idx gets no gradient
-        key = ("deferred", self.world * ids.numel(), g.shape[1], g.dtype, ids.device)
+        rdt = self.reduce_dtype if (self.reduce_dtype is not None and g.is_cuda) else g.dtype
+        key = ("deferred", self.world * ids.numel(), g.shape[1], rdt, ids.device)
         if key not in self._gather:
             self._gather[key] = (torch.empty(key[1], dtype=ids.dtype, device=ids.device),
-                                 torch.empty(key[1], key[2], dtype=g.dtype, device=g.device))
+                                 torch.empty(key[1], key[2], dtype=rdt, device=g.device))
         all_ids, all_rows = self._gather[key]
+        if all_rows.dtype != rows.dtype:
+            rows = rows.to(all_rows.dtype)
         dist.all_gather_into_tensor(all_ids, ids, group=self.group)
         dist.all_gather_into_tensor(all_rows, rows, group=self.group)
         for w in self._works:
             w.wait()  # the dense all-reduce (and everything else in flight) has landed on the current stream
+        self._join_comm()
         for buf in self._post:
             buf.div_(self.world)
         self._works, self._post = [], []
@@ -162,6 +208,7 @@ class GradReducer:
                         self._allreduce(m._proj_grad)
             for w in self._works:
                 w.wait()  # current stream waits for NCCL's
+            self._join_comm()
             for buf in self._post:
                 buf.div_(self.world)
         self._works = []

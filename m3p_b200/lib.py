@@ -119,6 +119,7 @@ PROTOTYPES = {
     "m3p_layernorm_bwd_cols": [POINTER(LnBwdArgs), c_void_p],
     "m3p_colsum_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p],
     "m3p_cast_f32_bf16": [c_void_p, c_void_p, c_int64, c_float, c_void_p],
+    "m3p_cast_bf16_f32": [c_void_p, c_void_p, c_int64, c_float, c_void_p],
     "m3p_sum_slabs_bf16": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p],
     "m3p_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     "m3p_permute_cast_f32_bf16": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
@@ -134,6 +135,7 @@ PROTOTYPES = {
     "m3p_rowdot_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                        c_void_p],
     "m3p_gather_rows_f32": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
+    "m3p_scatter_add_rows_bf16": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p],
     "m3p_scatter_add_rows_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p],
     "m3p_embed_fwd": [POINTER(EmbedArgs), c_void_p],
     "m3p_embed_bwd_route": [POINTER(EmbedBwdArgs), c_void_p],

@@ -186,6 +186,11 @@ def cast_f32_bf16(src, dst, n=None, scale=1.0):
     L.check(_lib().m3p_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), n, scale, _stream()), "m3p_cast_f32_bf16")
 
 
+def cast_bf16_f32(src, dst, n=None, scale=1.0):
+    n = src.numel() if n is None else n
+    L.check(_lib().m3p_cast_bf16_f32(src.data_ptr(), dst.data_ptr(), n, scale, _stream()), "m3p_cast_bf16_f32")
+
+
 def sum_slabs_bf16(src, n_slabs, slab_stride, dst, n):
     """dst = bf16(sum of the n_slabs fp32 slabs of src, in index order): deterministic split-K reduction."""
     L.check(_lib().m3p_sum_slabs_bf16(src.data_ptr(), n_slabs, slab_stride, dst.data_ptr(), n, _stream()),
@@ -256,6 +261,10 @@ def gather_rows_f32(table, idx, dst, n, d):
 
 
 def scatter_add_rows_f32(src, idx, skip_index, dst, n, d):
+    if src.dtype == torch.bfloat16:
+        L.check(_lib().m3p_scatter_add_rows_bf16(src.data_ptr(), idx.data_ptr(), skip_index, dst.data_ptr(), n, d,
+                                                 _stream()), "m3p_scatter_add_rows_bf16")
+        return
     L.check(_lib().m3p_scatter_add_rows_f32(src.data_ptr(), idx.data_ptr(), skip_index, dst.data_ptr(), n, d,
                                             _stream()), "m3p_scatter_add_rows_f32")
 
