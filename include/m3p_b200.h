@@ -237,6 +237,14 @@ M3P_API int m3p_gelu_bwd(const void* dg, const void* gp, void* du, int64_t n, m3
 M3P_API int m3p_permute_cast_f32_bf16(const float* in, void* out, int64_t A, int64_t B, int64_t F,
                                       m3p_stream_t stream);
 
+/* Device-side region pipeline (the reference does this on the host per sample,
+ * dataset_pretrain.py:258-292,379): regions flagged in zero_mask (B,R) are zeroed, every 2048-d row is L2-normalised
+ * (F.normalize, eps 1e-12; normalize = 0 skips it), and the result lands as the encoder's bf16 batch-major operand
+ * out (B,R,F).  in is (R,B,F) fp32 raw features.  ori (B,R,F) fp32, optional: the normalised UNMASKED rows — the
+ * MRFR regression target (xtrainer.py:2340). */
+M3P_API int m3p_region_prep(const float* in, const uint8_t* zero_mask, int32_t normalize, void* out, float* ori,
+                            int64_t R, int64_t B, int64_t F, m3p_stream_t stream);
+
 /* dst[i][:] = src[(f / n_inner) * stride_outer + (f % n_inner) * stride_inner ...], f = flat_idx[i]:
  * the boolean-mask row gather of predict() (transformer.py:1206) on a strided (slen, bs, d) view.
  * m3p_scatter_rows_bf16 is its adjoint for unique indices (dst pre-zeroed by the caller). */

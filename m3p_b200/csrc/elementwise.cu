@@ -863,6 +863,49 @@ permute_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ ou
   }
 }
 
+// Device-side half of the region pipeline the reference runs on the host per sample (dataset_pretrain.py:258-292,379):
+// zero the regions picked for masking, L2-normalise every 2048-d feature row (F.normalize, eps 1e-12), and hand the
+// encoder its bf16 batch-major operand — one pass over the raw features instead of host loops + an fp32 round trip.
+// One warp per (b, r) row.  in (R, B, F) fp32; out (B, R, F) bf16; ori (B, R, F) fp32 = the normalised UNMASKED
+// features (the MRFR regression target, xtrainer.py:2340), optional.
+__global__ void __launch_bounds__(EW_THREADS)
+region_prep_kernel(const float* __restrict__ in, const uint8_t* __restrict__ zero_mask, int normalize,
+                   __nv_bfloat16* __restrict__ out, float* __restrict__ ori, int R, int B, int F) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * EW_WARPS + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * EW_WARPS;
+  const long long rows = (long long)R * B;
+  const int nv = F >> 3;
+  for (long long o = warp0; o < rows; o += nwarps) {  // o = b * R + r (output-major)
+    const int b = (int)(o / R), r = (int)(o % R);
+    const float* src = in + ((long long)r * B + b) * F;
+    float ss = 0.f;
+    if (normalize) {
+      for (int c = lane; c < nv; c += 32) {
+        float v[8];
+        load8(src + c * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+      }
+      ss = warp_sum(ss);
+    }
+    const float sc = normalize ? 1.0f / fmaxf(sqrtf(ss), 1e-12f) : 1.0f;
+    const bool zero = zero_mask != nullptr && zero_mask[o] != 0;
+    for (int c = lane; c < nv; c += 32) {  // second read of the row hits L1/L2
+      float v[8];
+      load8(src + c * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= sc;
+      if (ori != nullptr) store8(ori + o * F + c * 8, v);
+      if (zero) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+      store8(out + o * F + c * 8, v);
+    }
+  }
+}
+
 // du = dg * gp (gp = gelu_erf'(u) stashed by the forward GEMM epilogue): backward of the GELU inside
 // BertPredictionHeadTransform (transformer.py:603-604), where the LayerNorm backward sits between the
 // next linear's dgrad and this activation.
@@ -1361,6 +1404,17 @@ extern "C" int m3p_permute_cast_f32_bf16(const float* in, void* out, int64_t A, 
   const long long cap = (long long)sm_count() * 16;
   permute_cast_kernel<<<(int)(g < cap ? g : cap), EW_THREADS, 0, stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out),
                                                                          (int)A, (int)B, (int)(F / 8));
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
+extern "C" int m3p_region_prep(const float* in, const uint8_t* zero_mask, int32_t normalize, void* out, float* ori,
+                               int64_t R, int64_t B, int64_t F, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(in && out, "m3p_region_prep: null pointer");
+  M3P_REQUIRE(R > 0 && B > 0 && F > 0 && F % 8 == 0, "m3p_region_prep: F must be a multiple of 8");
+  region_prep_kernel<<<ew_grid(R * B), EW_THREADS, 0, stream>>>(in, zero_mask, (int)normalize,
+                                                               reinterpret_cast<__nv_bfloat16*>(out), ori, (int)R, (int)B, (int)F);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }

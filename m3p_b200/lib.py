@@ -123,6 +123,7 @@ PROTOTYPES = {
     "m3p_sum_slabs_bf16": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p],
     "m3p_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     "m3p_permute_cast_f32_bf16": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
+    "m3p_region_prep": [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
     "m3p_gather_rows_bf16": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p],
     "m3p_scatter_rows_bf16": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p],
     "m3p_cross_entropy_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,

@@ -206,6 +206,11 @@ def permute_cast(src, dst, A, B, F):
             "m3p_permute_cast_f32_bf16")
 
 
+def region_prep(raw, zero_mask, normalize, out, ori, R, B, F):
+    L.check(_lib().m3p_region_prep(raw.data_ptr(), _p(zero_mask), int(normalize), out.data_ptr(), _p(ori), R, B, F,
+                                   _stream()), "m3p_region_prep")
+
+
 def gather_rows(src, flat_idx, n_inner, stride_outer, stride_inner, dst, n, d):
     L.check(_lib().m3p_gather_rows_bf16(src.data_ptr(), flat_idx.data_ptr(), n_inner, stride_outer, stride_inner,
                                         dst.data_ptr(), n, d, _stream()), "m3p_gather_rows_bf16")

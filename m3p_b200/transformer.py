@@ -455,10 +455,13 @@ class TransformerModel(nn.Module):
                              "move the model and inputs to cuda)" % t.device)
 
     def jointfwd(self, x, lengths, x_img, lengths_img, causal=False, positions=None, langs=None, image_loc=None,
-                 refine_image=False, is_latent=False, text_embed=None):
+                 refine_image=False, is_latent=False, text_embed=None, image_prep=None):
         """Image regions ++ text tokens through the encoder — transformer.py:878-968.
         x (T,B) int64, x_img (R,B,2048), image_loc (R,B,5) -> (R+T, B, dim).  `langs`/`positions` are
-        accepted and ignored exactly as the reference does (:932-938)."""
+        accepted and ignored exactly as the reference does (:932-938).
+        `image_prep` (extension): dict(normalize=True, zero_mask=(B,R) bool, ori_out=(B,R,2048) fp32 or
+        None) — x_img then holds RAW region features and the masking / L2-normalisation the reference's dataset does
+        on the host (dataset_pretrain.py:258-292,379) runs inside the cast kernel."""
         if causal or refine_image or is_latent:
             raise NotImplementedError("jointfwd: causal / refine_image / is_latent are outside the B200 path")
         slen, bs = x.size()
@@ -466,8 +469,10 @@ class TransformerModel(nn.Module):
         assert image_loc is not None
         self._require_cuda(x)
         spec = dict(kind="joint", B=bs, T=slen, R=x_img.size(0), x=x, lengths=lengths + lengths_img, x_img=x_img,
-                    image_loc=image_loc, positions=None, langs=None,
+                    image_loc=image_loc, positions=None, langs=None, image_prep=image_prep,
                     flags=L.M3P_EMB_POS | L.M3P_EMB_MASK_PRE | L.M3P_EMB_LN | L.M3P_EMB_DROP2)
+        if image_prep is not None and x_img.requires_grad:
+            raise NotImplementedError("image_prep with d x_img (FreeLB) is not supported: perturb the prepared features")
         return _EncoderFn.run(self, spec, x_img, text_embed)
 
     def fwd(self, x, lengths, causal, src_enc=None, src_len=None, positions=None, langs=None, cache=None,
@@ -607,7 +612,15 @@ class TransformerModel(nn.Module):
             if xi.dtype != _F32 or not xi.is_contiguous():
                 xi = xi.to(_F32).contiguous()
             ximg16 = e(B * R, FEAT_DIM)
-            ops.permute_cast(xi, ximg16, R, B, FEAT_DIM)  # (R,B,F) fp32 -> (B,R,F) bf16
+            prep = spec.get("image_prep")
+            if prep is None:
+                ops.permute_cast(xi, ximg16, R, B, FEAT_DIM)  # (R,B,F) fp32 -> (B,R,F) bf16
+            else:
+                # raw region features: zero the masked regions, L2-normalise, cast + permute in one pass (8f3)
+                zm = prep.get("zero_mask")
+                zm = None if zm is None else zm.to(device=dev, dtype=torch.uint8).contiguous()
+                ori = prep.get("ori_out")
+                ops.region_prep(xi, zm, prep.get("normalize", True), ximg16, ori, R, B, FEAT_DIM)
             e_img = e(B * R, d, dt=_F32)
             ops.linear(ximg16, self._w16("image_embeddings.image_embeddings.weight"),
                        self._w32("image_embeddings.image_embeddings.bias"), e_img, out_f32=True)
