@@ -113,6 +113,16 @@ typedef struct m3p_gemm_args {
    * and stores the pre-LayerNorm sum in fp32, so the residual stream is never rounded to bf16
    * (transformer.py:951-952,956 run in fp32 in the reference). */
   int32_t aux_f32;
+  /* optional, fp32 residual epilogue only: aux then holds the PRE-LayerNorm sum x of the previous sub-layer and the
+   * residual is recomputed in the epilogue as rowmask * ((x - mean[row]) * rstd[row] * gamma[col] + beta[col])
+   * (rowmask(row) = (row % S) < seqlen[row / S]; seqlen = NULL: no mask) — the LayerNorm output never has to exist
+   * in fp32 (transformer.py:951-953, 956-958: `tensor = layer_norm(tensor + ...)` feeding the next residual add). */
+  const float* aux_ln_mean;
+  const float* aux_ln_rstd;
+  const float* aux_ln_gamma;
+  const float* aux_ln_beta;
+  const int32_t* aux_ln_seqlen;
+  int64_t aux_ln_S;
 } m3p_gemm_args;
 
 M3P_API int m3p_gemm_bf16(const m3p_gemm_args* args, m3p_stream_t stream);

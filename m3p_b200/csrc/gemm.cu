@@ -68,6 +68,11 @@ struct GemmKernelParams {
   int tma_store;  // bf16 outputs leave through smem staging + cp.async.bulk.tensor stores
   float* colsum;  // optional [N]: += column sums of the stored (bf16-rounded) output
   long long split_stride;  // fp32 output, split_k > 1, !accumulate: K split ks stores its partial at out + ks * split_stride
+  // fp32 residual epilogue, optional: the aux tile holds the PRE-LayerNorm sum of the previous sub-layer and the residual
+  // is recomputed here as rowmask * ((aux - mean[row]) * rstd[row] * gamma[col] + beta[col]) — the LayerNorm kernel then
+  // only writes its bf16 operand copy, never an fp32 copy of its output
+  const float* ln_mean; const float* ln_rstd; const float* ln_gamma; const float* ln_beta;
+  const int32_t* ln_seqlen; long long ln_S;
 };
 
 // Unit order: K split fastest, then the tile dimension with FEWER tiles.  Units that are adjacent in this order
@@ -153,6 +158,20 @@ constexpr bool f32_ring() { return OUT_F32 && EPI == M3P_EPI_DROP_RES; }
 // v = epilogue(alpha * acc + bias [, x]) for 16 columns of one row; gq = gelu(.) for M3P_EPI_GELU (v = gelu').
 // x: the chunk's aux values (residual / stashed gelu' / tanh output); e0: row-major element index of the chunk's
 // first element (dropout counter).
+// residual = LayerNorm(aux) recomputed on the fly (see GemmKernelParams::ln_mean): a = rstd, b = -mean * rstd of this
+// thread's row (a = 0 for rows removed by the mask, which also kills beta through `on`)
+__device__ __forceinline__ void ln_residual16(float* x, const float* sgamma, const float* sbeta, float a, float b, float on) {
+#pragma unroll
+  for (int j = 0; j < EW / 4; ++j) {
+    const float4 g = *reinterpret_cast<const float4*>(sgamma + 4 * j);
+    const float4 be = *reinterpret_cast<const float4*>(sbeta + 4 * j);
+    x[4 * j + 0] = fmaf(fmaf(x[4 * j + 0], a, b), g.x, be.x * on);
+    x[4 * j + 1] = fmaf(fmaf(x[4 * j + 1], a, b), g.y, be.y * on);
+    x[4 * j + 2] = fmaf(fmaf(x[4 * j + 2], a, b), g.z, be.z * on);
+    x[4 * j + 3] = fmaf(fmaf(x[4 * j + 3], a, b), g.w, be.w * on);
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_math(const GemmKernelParams& p, const uint32_t* acc, const float* sbias,
                                               const float* x, uint32_t e0, uint32_t seed_lo, uint32_t seed_hi,
@@ -211,6 +230,14 @@ __device__ __forceinline__ void epilogue_chunk_direct(const GemmKernelParams& p,
     const float* ap = reinterpret_cast<const float*>(p.aux) + row * p.ldaux + col0;
 #pragma unroll
     for (int j = 0; j < EW; ++j) x[j] = (j < ncols) ? ap[j] : 0.f;
+    if (p.ln_mean != nullptr) {
+      bool on = true;
+      if (p.ln_seqlen != nullptr) on = (row % p.ln_S) < p.ln_seqlen[row / p.ln_S];
+      const float a = on ? p.ln_rstd[row] : 0.f, b = on ? -p.ln_mean[row] * a : 0.f;
+#pragma unroll
+      for (int j = 0; j < EW; ++j)
+        if (j < ncols) x[j] = on ? fmaf(fmaf(x[j], a, b), p.ln_gamma[col0 + j], p.ln_beta[col0 + j]) : 0.f;
+    }
   } else if constexpr (epi_has_aux<EPI>()) {
     const __nv_bfloat16* ap = p.aux + row * p.ldaux + col0;
     if (full) {
@@ -284,7 +311,8 @@ struct GemmCfg {
   static constexpr uint32_t B_BYTES = BN_LOAD * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
-  static constexpr uint32_t BIAS_BYTES = EPI_WARPS * (BN / 2) * 4;
+  // per epilogue warp: its slice of the bias (+ gamma and beta of the recomputed residual LayerNorm)
+  static constexpr uint32_t BIAS_BYTES = EPI_WARPS * (BN / 2) * 4 * (f32_ring<EPI, OUT_F32>() ? 3 : 1);
   // Staging for the TMA epilogue: per epilogue warp a ring of [32 rows][32 cols] bf16 tiles per output.  Epilogues
   // with an aux operand TMA-LOAD the aux tile into the ring slot two groups ahead, overwrite it in place with the
   // result and TMA-STORE it (ring of 3); the others only store (ring of 2).
@@ -477,7 +505,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr bool HAS_AUX = epi_has_aux<EPI>();
     constexpr int RING = Cfg::RING;
     const int cbase = half * (BN / 2);
-    float* sbias = bias_smem + ew * (BN / 2);
+    float* sbias = bias_smem + ew * (BN / 2) * (F32R ? 3 : 1);
+    float* sgamma = sbias + BN / 2;   // F32R only
+    float* sbeta = sgamma + BN / 2;
     uint8_t* ring = stg_smem + ew * Cfg::WARP_STG;  // slot b, output o at ring + (b * N_OUT + o) * STG_TILE
     uint64_t* my_aux_bar = aux_bar + ew * AUX_RING_MAX;
     const bool use_tma = (!OUT_F32 || F32R) && p.tma_store;
@@ -543,6 +573,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
         *reinterpret_cast<float4*>(sbias + c) = b;
+        if constexpr (F32R) {
+          if (p.ln_mean != nullptr) {  // N is a multiple of 4 and col < N whenever this tile has work (checked on the host)
+            const bool in = col + 3 < p.N;
+            *reinterpret_cast<float4*>(sgamma + c) = in ? __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(sbeta + c) = in ? __ldg(reinterpret_cast<const float4*>(p.ln_beta + col))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      float ln_a = 0.f, ln_b = 0.f, ln_on = 0.f;  // this thread's row: rstd, -mean * rstd, 1 (all 0 for masked rows)
+      if constexpr (F32R) {
+        if (p.ln_mean != nullptr && row_ok) {
+          bool on = true;
+          if (p.ln_seqlen != nullptr) on = (row % p.ln_S) < p.ln_seqlen[row / p.ln_S];
+          if (on) {
+            ln_a = __ldg(p.ln_rstd + row);
+            ln_b = -__ldg(p.ln_mean + row) * ln_a;
+            ln_on = 1.f;
+          }
+        }
       }
       __syncwarp();
       GT_MARK();  // epi: bias staged
@@ -578,8 +629,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tmem_ld_wait16(acc[ii]);
             if (i + 1 < NCH) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
             float v[EW], gq[EW], x[EW];
-            if constexpr (F32R) unstage_f32x16(slot, lane, x);
-            else if constexpr (HAS_AUX) unstage_bf16x16(slot, lane, ci, x);
+            if constexpr (F32R) {
+              unstage_f32x16(slot, lane, x);
+              if (p.ln_mean != nullptr) ln_residual16(x, sgamma + i * EW, sbeta + i * EW, ln_a, ln_b, ln_on);
+            } else if constexpr (HAS_AUX) {
+              unstage_bf16x16(slot, lane, ci, x);
+            }
             const uint32_t e0 = static_cast<uint32_t>(row) * static_cast<uint32_t>(p.N) +
                                 static_cast<uint32_t>(gcol0 + ci * EW);
             epilogue_math<EPI>(p, acc[ii], sbias + i * EW, x, e0, seed_lo, seed_hi, v, gq);
@@ -816,6 +871,13 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   p.accumulate = a->accumulate;
   p.colsum = a->colsum;
   p.split_stride = a->split_stride;
+  M3P_REQUIRE(a->aux_ln_mean == nullptr || (f32r && a->aux_ln_rstd && a->aux_ln_gamma && a->aux_ln_beta && a->n % 4 == 0 &&
+                                            aligned16(a->aux_ln_gamma) && aligned16(a->aux_ln_beta) &&
+                                            (a->aux_ln_seqlen == nullptr || a->aux_ln_S > 0)),
+              "m3p_gemm_bf16: aux_ln_* needs the fp32 residual epilogue, all four arrays (16-byte aligned gamma / beta), "
+              "n %% 4 == 0 and S > 0 with a row mask");
+  p.ln_mean = a->aux_ln_mean; p.ln_rstd = a->aux_ln_rstd; p.ln_gamma = a->aux_ln_gamma; p.ln_beta = a->aux_ln_beta;
+  p.ln_seqlen = a->aux_ln_seqlen; p.ln_S = a->aux_ln_S;
   {
     const int osz = a->out_f32 ? 4 : 2;
     bool ok = aligned16(a->out) && ((a->ldo * osz) % 16 == 0);

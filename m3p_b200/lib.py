@@ -33,6 +33,8 @@ class GemmArgs(ctypes.Structure):
         ("colsum", c_void_p),
         ("split_stride", c_int64),
         ("aux_f32", c_int32),
+        ("aux_ln_mean", c_void_p), ("aux_ln_rstd", c_void_p), ("aux_ln_gamma", c_void_p), ("aux_ln_beta", c_void_p),
+        ("aux_ln_seqlen", c_void_p), ("aux_ln_S", c_int64),
     ]
 
 

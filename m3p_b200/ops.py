@@ -77,7 +77,7 @@ def split_k_for(m, n, k):
 
 def gemm(a, b, m, n, k, out, *, lda=None, ldb=None, ldo=None, a_mn=False, b_mn=False, epi=L.M3P_EPI_LINEAR,
          out_f32=False, accumulate=False, split_k=1, alpha=1.0, bias=None, out2=None, ldo2=None, aux=None,
-         ldaux=None, drop_p=0.0, seed=0, colsum=None, split_stride=0):
+         ldaux=None, drop_p=0.0, seed=0, colsum=None, split_stride=0, aux_ln=None):
     """C[m][n] = sum_k A(m,k) B(n,k) with a fused epilogue (see m3p_gemm_bf16 in the header)."""
     g = L.GemmArgs()
     g.a, g.b = a.data_ptr(), b.data_ptr()
@@ -101,6 +101,10 @@ def gemm(a, b, m, n, k, out, *, lda=None, ldb=None, ldo=None, a_mn=False, b_mn=F
     g.colsum = _p(colsum)
     g.split_stride = split_stride
     g.aux_f32 = int(aux is not None and aux.dtype == torch.float32)
+    if aux_ln is not None:  # (mean, rstd, gamma, beta, seqlen or None, S): the residual is LayerNorm(aux), recomputed
+        g.aux_ln_mean, g.aux_ln_rstd = aux_ln[0].data_ptr(), aux_ln[1].data_ptr()
+        g.aux_ln_gamma, g.aux_ln_beta = aux_ln[2].data_ptr(), aux_ln[3].data_ptr()
+        g.aux_ln_seqlen, g.aux_ln_S = _p(aux_ln[4]), aux_ln[5]
     L.check(_lib().m3p_gemm_bf16(_byref(g), _stream()), "m3p_gemm_bf16")
     return out
 

@@ -657,9 +657,11 @@ class TransformerModel(nn.Module):
         a.seqlen = seqlen.data_ptr()
         a.ln_emb_g = self._w32("layer_norm_emb.weight").data_ptr()
         a.ln_emb_b = self._w32("layer_norm_emb.bias").data_ptr()
-        # residual stream: every LayerNorm output exists twice — the bf16 copy the tensor cores read (h) and the
-        # fp32 copy the next residual add reads (h32); the pre-LayerNorm sums x1 / x2 are fp32 only.  Nothing on the
-        # residual path is ever rounded to bf16 (the reference adds in fp32, transformer.py:951-952,956).
+        # residual stream: the pre-LayerNorm sums x1 / x2 are fp32; a LayerNorm kernel only writes the bf16 copy the
+        # tensor cores read (h), and the residual add of the NEXT linear recomputes the fp32 LayerNorm output from the
+        # stored sum, mean, rstd, gamma, beta in its GEMM epilogue (res_ln).  Only the embedding output exists as an
+        # fp32 tensor (h32).  Nothing on the residual path is ever rounded to bf16 (the reference adds in fp32,
+        # transformer.py:951-952,956).
         h, h32 = e(M, d), e(M, d, dt=_F32)
         if spec["flags"] & L.M3P_EMB_LN:
             y_pre, emb_mean, emb_rstd = e(M, d, dt=_F32), e(M, dt=_F32), e(M, dt=_F32)
@@ -671,6 +673,8 @@ class TransformerModel(nn.Module):
 
         # ---- layer loop (transformer.py:947-958) ----
         scale = 1.0 / math.sqrt(d // H)
+        res, res_ln = h32, None  # what the next residual add reads: an fp32 tensor, or (pre-LN sum, LayerNorm recipe)
+        recompute = os.environ.get("M3P_RES_LN", "1") != "0"  # 0: LayerNorm kernels also write an fp32 copy (A/B runs)
         for i in range(self.n_layers):
             w = self._layer_views(i)
             s1, s2, sa = seed ^ (0x100 * (i + 1) + 1), seed ^ (0x100 * (i + 1) + 2), seed ^ (0x100 * (i + 1) + 3)
@@ -679,21 +683,27 @@ class TransformerModel(nn.Module):
             ctx, lse = e(M, d), e(B * H * S, dt=_F32)
             ops.attention_fwd(qkv, seqlen, B, S, H, scale, p_att, sa, ctx, lse)
             x1 = e(M, d, dt=_F32)
-            ops.linear(ctx, w["wo"], w["bo"], x1, epi=L.M3P_EPI_DROP_RES, aux=h32, drop_p=p_drop, seed=s1, out_f32=True)
-            h1, h1_32, mean1, rstd1 = e(M, d), e(M, d, dt=_F32), e(M, dt=_F32), e(M, dt=_F32)
+            ops.linear(ctx, w["wo"], w["bo"], x1, epi=L.M3P_EPI_DROP_RES, aux=res, aux_ln=res_ln, drop_p=p_drop, seed=s1,
+                       out_f32=True)
+            h1, mean1, rstd1 = e(M, d), e(M, dt=_F32), e(M, dt=_F32)
+            h1_32 = None if recompute else e(M, d, dt=_F32)
             ops.layernorm_fwd(x1, w["g1"], w["b1"], h1, mean1, rstd1, LN_EPS, y32=h1_32)
             gp, g = e(M, 4 * d), e(M, 4 * d)  # gelu'(u) (stash for the backward) and gelu(u)
             ops.linear(h1, w["w1"], w["bb1"], gp, epi=L.M3P_EPI_GELU, out2=g)
             x2 = e(M, d, dt=_F32)
-            ops.linear(g, w["w2"], w["bb2"], x2, epi=L.M3P_EPI_DROP_RES, aux=h1_32, drop_p=p_drop, seed=s2, out_f32=True)
+            if recompute:
+                ops.linear(g, w["w2"], w["bb2"], x2, epi=L.M3P_EPI_DROP_RES, aux=x1,
+                           aux_ln=(mean1, rstd1, w["g1"], w["b1"], None, 0), drop_p=p_drop, seed=s2, out_f32=True)
+            else:
+                ops.linear(g, w["w2"], w["bb2"], x2, epi=L.M3P_EPI_DROP_RES, aux=h1_32, drop_p=p_drop, seed=s2, out_f32=True)
             hn, mean2, rstd2 = e(M, d), e(M, dt=_F32), e(M, dt=_F32)
-            hn32 = e(M, d, dt=_F32) if i + 1 < self.n_layers else None  # the last layer's output has no residual reader
+            hn32 = None if (recompute or i + 1 == self.n_layers) else e(M, d, dt=_F32)
             ops.layernorm_fwd(x2, w["g2"], w["b2"], hn, mean2, rstd2, LN_EPS, seqlen=seqlen, S=S, y32=hn32)
+            res, res_ln = (x2, (mean2, rstd2, w["g2"], w["b2"], seqlen, S)) if recompute else (hn32, None)
             if need_grad:
                 st["layers"].append(dict(h=h, qkv=qkv, ctx=ctx, lse=lse, x1=x1, h1=h1, mean1=mean1, rstd1=rstd1, gp=gp,
                                          g=g, x2=x2, mean2=mean2, rstd2=rstd2, s1=s1, s2=s2, sa=sa))
-            h, h32 = hn, hn32
-            del h1_32
+            h = hn
         return h, st
 
     def _encode_backward(self, st, dh, want_dximg, want_dtext):

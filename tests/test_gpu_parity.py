@@ -999,6 +999,40 @@ def test_gemm_fused_epilogues(m3p):
     assert _rel(o, torch.tanh(0.1 * (ref - bias) + bias)) < KERNEL_TOL
 
 
+@pytest.mark.parametrize("m,n,k,masked", [(300, 392, 200, True), (14592, 768, 768, True), (7296, 768, 3072, False)])
+def test_gemm_fp32_residual_epilogue(m3p, m, n, k, masked):
+    """M3P_EPI_DROP_RES with out_f32 / aux_f32: out = aux + (A B^T + bias) in fp32 — the encoder's residual stream —
+    with a plain fp32 residual and with the residual recomputed in the epilogue as rowmask * LayerNorm(aux)
+    (aux_ln_*), ragged M / N edges and the step's own shapes included; bit-reproducible."""
+    from m3p_b200 import lib as L, ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = (torch.randn(m, k, device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn(n, k, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(n, device="cuda", generator=g)
+    aux = torch.randn(m, n, device="cuda", generator=g) * 2.0 + 0.3
+    ref = A.float() @ B.float().t() + bias
+    out = torch.empty(m, n, device="cuda")
+    ops.gemm(A, B, m, n, k, out, bias=bias, epi=L.M3P_EPI_DROP_RES, aux=aux, out_f32=True)
+    assert _rel(out, ref + aux) < 1e-5
+    S = 19 if m % 19 == 0 else (228 if m % 228 == 0 else m)
+    seqlen = torch.randint(S // 3, S + 1, (m // S,), device="cuda", dtype=torch.int32) if masked and S != m else None
+    gam, bet = torch.randn(n, device="cuda", generator=g), torch.randn(n, device="cuda", generator=g)
+    mean, var = aux.mean(-1), aux.var(-1, unbiased=False)
+    rstd = torch.rsqrt(var + 1e-12)
+    res = F.layer_norm(aux, (n,), gam, bet, 1e-12)
+    if seqlen is not None:
+        res = res * (torch.arange(S, device="cuda")[None] < seqlen[:, None]).reshape(m, 1)
+    out2, out3 = torch.empty(m, n, device="cuda"), torch.empty(m, n, device="cuda")
+    for o in (out2, out3):
+        ops.gemm(A, B, m, n, k, o, bias=bias, epi=L.M3P_EPI_DROP_RES, aux=aux, out_f32=True,
+                 aux_ln=(mean, rstd, gam, bet, seqlen, S if seqlen is not None else 0))
+    assert _rel(out2, ref + res) < 1e-5 and torch.equal(out2, out3)
+    ops.gemm(A, B, m, n, k, out3, bias=bias, epi=L.M3P_EPI_DROP_RES, aux=aux, out_f32=True, drop_p=0.2, seed=9,
+             aux_ln=(mean, rstd, gam, bet, seqlen, S if seqlen is not None else 0))
+    kept = ((out3 - res).abs() > 1e-6).float().mean().item()
+    assert abs(kept - 0.8) < 0.02
+
+
 def test_cuda_graph_step_matches_eager_and_redraws_dropout(m3p):
     """GraphedStep: the captured step reproduces the eager gradients, accepts new inputs, and — because the
     dropout seeds live in a device word bumped inside the graph — draws new masks on every replay."""
