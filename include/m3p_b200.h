@@ -285,6 +285,13 @@ M3P_API int m3p_masked_mse_bwd(const void* pred, int64_t ld, const float* target
                                const float* grad_scale, void* dpred, int64_t ldd, int64_t n, int64_t d,
                                m3p_stream_t stream);
 
+/* ITM loss of pretrain_under_step / t2i_step / i2t_step (xtrainer.py:2359-2372, 1917-1942) on the
+ * n_groups * sample_n matching scores, value and gradient in one launch:
+ *   *loss = w_multi * CE(scores.view(-1, sample_n), pos_labels) + w_bin * BCEWithLogits(scores.view(-1), onehot(pos))
+ *   dscores = d loss / d scores (the caller scales it by the upstream gradient). */
+M3P_API int m3p_relation_loss(const float* scores, const int64_t* pos_labels, int64_t n_groups, int64_t sample_n,
+                              float w_multi, float w_bin, float* loss, float* dscores, m3p_stream_t stream);
+
 /* seq_relationship / seq_relationship2: Linear(d, 1) (transformer.py:713,716,1196,1200) and backward.
  * tanh_grad != 0: x is the BertPooler tanh output (:556-557) and dx is returned w.r.t. the
  * pre-activation, dx = dout * w * (1 - x^2). */

@@ -1141,6 +1141,47 @@ mse_bwd_kernel(const __nv_bfloat16* __restrict__ pred, long long ld, const float
 }
 
 // =================================================================================================
+// ITM loss of pretrain_under_step / t2i_step (xtrainer.py:2359-2372, 1917-1942) on the B = n_groups * sample_n
+// matching scores, forward AND gradient in one launch (the eager version is ~30 one-microsecond kernels in the
+// middle of the step):
+//   loss = w_multi * mean_g( logsumexp(s_g) - s_g[pos_g] ) + w_bin * mean_i( BCEWithLogits(s_i, onehot_i) )
+//   dscores_i = w_multi * (softmax_g(s)_i - onehot_i) / n_groups + w_bin * (sigmoid(s_i) - onehot_i) / B
+// One CTA; thread t owns group t, t + blockDim, ...; the two means are reduced in a fixed order.
+// =================================================================================================
+__global__ void relation_loss_kernel(const float* __restrict__ scores, const int64_t* __restrict__ pos, int n_groups,
+                                     int sample_n, float w_multi, float w_bin, float* __restrict__ loss,
+                                     float* __restrict__ dscores) {
+  __shared__ float s_ce[32], s_bce[32];
+  float ce = 0.f, bce = 0.f;
+  const float inv_g = 1.0f / (float)n_groups, inv_b = 1.0f / ((float)n_groups * (float)sample_n);
+  for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
+    const float* sg = scores + (long long)g * sample_n;
+    const int p = (int)pos[g];
+    float mx = -INFINITY;
+    for (int j = 0; j < sample_n; ++j) mx = fmaxf(mx, sg[j]);
+    float sum = 0.f;
+    for (int j = 0; j < sample_n; ++j) sum += expf(sg[j] - mx);
+    const float lse = mx + logf(sum);
+    ce += lse - sg[p];
+    for (int j = 0; j < sample_n; ++j) {
+      const float x = sg[j], y = (j == p) ? 1.f : 0.f;
+      bce += fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));
+      const float sig = 1.0f / (1.0f + expf(-x));
+      dscores[(long long)g * sample_n + j] = w_multi * (expf(x - lse) - y) * inv_g + w_bin * (sig - y) * inv_b;
+    }
+  }
+  ce = warp_sum(ce);
+  bce = warp_sum(bce);
+  if ((threadIdx.x & 31) == 0) { s_ce[threadIdx.x >> 5] = ce; s_bce[threadIdx.x >> 5] = bce; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_ce[w]; b += s_bce[w]; }
+    *loss = w_multi * a * inv_g + w_bin * b * inv_b;
+  }
+}
+
+// =================================================================================================
 // tiny linear d -> 1 (seq_relationship, transformer.py:713,1196) and its backward
 // =================================================================================================
 __global__ void __launch_bounds__(EW_THREADS)
@@ -1160,11 +1201,14 @@ __global__ void __launch_bounds__(EW_THREADS)
 rowdot_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                   __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long long rows, int d,
                   int tanh_grad) {
+  // grid (column blocks, row blocks of 16): a dependent load per row made the single-pass loop latency-bound
   const int j = blockIdx.x * EW_THREADS + threadIdx.x;
   if (j >= d) return;
   float acc = 0.f, accb = 0.f;
   const float wj = w[j];
-  for (long long r = 0; r < rows; ++r) {
+  const long long r_lo = (long long)blockIdx.y * 16, r_hi = r_lo + 16 < rows ? r_lo + 16 : rows;
+#pragma unroll 4
+  for (long long r = r_lo; r < r_hi; ++r) {
     const float g = dout[r];
     const float xv = __bfloat162float(x[r * d + j]);
     acc += g * xv;
@@ -1501,6 +1545,18 @@ extern "C" int m3p_masked_mse_bwd(const void* pred, int64_t ld, const float* tar
   return M3P_OK;
 }
 
+extern "C" int m3p_relation_loss(const float* scores, const int64_t* pos_labels, int64_t n_groups, int64_t sample_n,
+                                 float w_multi, float w_bin, float* loss, float* dscores, m3p_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  M3P_REQUIRE(scores && pos_labels && loss && dscores, "m3p_relation_loss: null pointer");
+  M3P_REQUIRE(n_groups > 0 && sample_n > 0 && n_groups < (1 << 24) && sample_n <= 4096, "m3p_relation_loss: bad shape");
+  const int threads = n_groups >= 1024 ? 1024 : (int)((n_groups + 31) / 32 * 32);
+  relation_loss_kernel<<<1, threads, 0, stream>>>(scores, pos_labels, (int)n_groups, (int)sample_n, w_multi, w_bin, loss,
+                                                  dscores);
+  M3P_CUDA_OK(cudaGetLastError());
+  return M3P_OK;
+}
+
 extern "C" int m3p_rowdot_fwd(const void* x, const float* w, const float* bias, float* out, int64_t rows, int64_t d,
                               m3p_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -1515,7 +1571,7 @@ extern "C" int m3p_rowdot_bwd(const float* dout, const void* x, const float* w, 
                               int64_t rows, int64_t d, int32_t tanh_grad, m3p_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   M3P_REQUIRE(dout && x && w && dx && dw && db && rows > 0 && d > 0, "m3p_rowdot_bwd: bad arguments");
-  rowdot_bwd_kernel<<<(unsigned)((d + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, stream>>>(
+  rowdot_bwd_kernel<<<dim3((unsigned)((d + EW_THREADS - 1) / EW_THREADS), (unsigned)((rows + 15) / 16)), EW_THREADS, 0, stream>>>(
       dout, reinterpret_cast<const __nv_bfloat16*>(x), w, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, rows, (int)d,
       (int)tanh_grad);
   M3P_CUDA_OK(cudaGetLastError());

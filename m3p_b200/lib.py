@@ -134,6 +134,7 @@ PROTOTYPES = {
                               c_void_p, c_int64, c_void_p],
     "m3p_masked_mse_fwd": [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p],
     "m3p_masked_mse_bwd": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
+    "m3p_relation_loss": [c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p],
     "m3p_rowdot_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
     "m3p_rowdot_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                        c_void_p],

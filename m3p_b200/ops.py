@@ -254,6 +254,11 @@ def masked_mse_bwd(pred, target, weight, grad_scale, dpred):
             "m3p_masked_mse_bwd")
 
 
+def relation_loss(scores, pos_labels, sample_n, w_multi, w_bin, loss, dscores):
+    L.check(_lib().m3p_relation_loss(scores.data_ptr(), pos_labels.data_ptr(), pos_labels.numel(), sample_n, w_multi, w_bin,
+                                     loss.data_ptr(), dscores.data_ptr(), _stream()), "m3p_relation_loss")
+
+
 def rowdot_fwd(x, w, bias, out):
     L.check(_lib().m3p_rowdot_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1],
                                   _stream()), "m3p_rowdot_fwd")

@@ -62,8 +62,32 @@ def masked_mse(pred, target, weight):
     return _MaskedMse.apply(pred.contiguous(), target.contiguous(), weight.contiguous())
 
 
+class _RelationLoss(torch.autograd.Function):
+    """The ITM loss and its gradient in one kernel (m3p_relation_loss)."""
+
+    @staticmethod
+    def forward(ctx, scores, pos_labels, sample_n, w_multi, w_bin):
+        from . import ops
+        ops.use_current_stream()
+        s = scores.reshape(-1).to(torch.float32).contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=s.device)
+        ds = torch.empty_like(s)
+        ops.relation_loss(s, pos_labels.contiguous(), sample_n, w_multi, w_bin, loss, ds)
+        ctx.save_for_backward(ds)
+        ctx.shape = scores.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (ds,) = ctx.saved_tensors
+        return (ds * dloss).view(ctx.shape), None, None, None, None
+
+
 def relation_loss(scores, pos_labels, sample_n, w_multi=1.0, w_bin=1.0):
-    """xtrainer.py:2359-2372 / 1917-1942: CE over groups of sample_n + BCE against the one-hot positive."""
+    """xtrainer.py:2359-2372 / 1917-1942: CE over groups of sample_n + BCE against the one-hot positive (one kernel
+    on the device; the same expression in torch for CPU tensors)."""
+    if scores.is_cuda:
+        return _RelationLoss.apply(scores, pos_labels, sample_n, float(w_multi), float(w_bin))
     ce = F.cross_entropy(scores.view(-1, sample_n), pos_labels)
     onehot = F.one_hot(pos_labels, sample_n).to(scores.dtype)
     bce = F.binary_cross_entropy_with_logits(scores.view(-1), onehot.view(-1))

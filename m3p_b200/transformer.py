@@ -131,6 +131,7 @@ class TransformerModel(nn.Module):
         # gradients): lets refresh_operands() / zero_grad() skip work that has already been done
         self._operands_valid = False
         self._emb16_valid = False
+        self._emb16_event = None  # set by _start_operand_refresh when the projection matrix is being cast on the side stream
         self._grads_clean = False
         self._build_parameters()
         from .optim import tag_parameters
@@ -308,6 +309,7 @@ class TransformerModel(nn.Module):
         self._emb_grad = None
         self._proj_grad = None
         self._emb_touched, self._emb_dense_dirty = None, True
+        self._emb16_event = None
         self.invalidate_operands()
         self._grads_clean = False
 
@@ -352,10 +354,50 @@ class TransformerModel(nn.Module):
             if self._flat16 is None:
                 self._flat16 = torch.empty(self._flat_numel, dtype=_BF16, device=self._flat.device)
             ops.cast_f32_bf16(self._flat, self._flat16, self._flat_numel)
-        if embeddings and (self._emb16 is None or not self._emb16_valid):
-            if self._emb16 is None:
-                self._emb16 = torch.empty(self._proj.shape, dtype=_BF16, device=self._flat.device)
-            ops.cast_f32_bf16(self._proj.data, self._emb16, self._proj.numel())
+        if embeddings:
+            ev, self._emb16_event = self._emb16_event, None
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)  # cast by _start_operand_refresh on the side stream
+            elif self._emb16 is None or not self._emb16_valid:
+                if self._emb16 is None:
+                    self._emb16 = torch.empty(self._proj.shape, dtype=_BF16, device=self._flat.device)
+                ops.cast_f32_bf16(self._proj.data, self._emb16, self._proj.numel())
+
+    def _start_operand_refresh(self):
+        """The encoder forward's version of refresh_operands(): the cast of everything the first layer does not need
+        (layers 1.., the heads and — if the MLM head ran in the previous step — the V x d projection matrix, 0.55 + 1.15
+        GB of pure HBM traffic) goes to the side stream underneath the embedding stage and layer 0; `_encode` waits
+        for it before layer 1, the MLM head before its GEMM.  Returns the event to wait for (or None)."""
+        ops.use_current_stream()
+        dev = self._flat.device
+        self._emb16_event = None  # a previous forward's cast finished long ago (its event was joined in _encode)
+        need_flat = self._flat16 is None or not self._operands_valid
+        need_emb = self.with_output and self._emb16 is not None and not self._emb16_valid
+        if not (need_flat or need_emb):
+            return None
+        if self._flat16 is None:
+            self._flat16 = torch.empty(self._flat_numel, dtype=_BF16, device=dev)
+        split = self._segments["layer1"][0] if self.n_layers > 1 else self._flat_numel
+        if not self.overlap_grads:
+            split = self._flat_numel
+        if need_flat:
+            ops.cast_f32_bf16(self._flat, self._flat16, split)
+        ev_rest = None
+        if (need_flat and split < self._flat_numel) or need_emb:
+            cur, side = torch.cuda.current_stream(), self._side_stream_for(dev)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            side.wait_event(fork)
+            with torch.cuda.stream(side), ops.on_stream(side):
+                if need_flat and split < self._flat_numel:
+                    ops.cast_f32_bf16(self._flat[split:], self._flat16[split:], self._flat_numel - split)
+                    ev_rest = torch.cuda.Event()
+                    ev_rest.record(side)
+                if need_emb:
+                    ops.cast_f32_bf16(self._proj.data, self._emb16, self._proj.numel())
+                    self._emb16_event = torch.cuda.Event()
+                    self._emb16_event.record(side)
+        return ev_rest
 
     def attach_grads(self, zero=False):
         """Make every hot `param.grad` a view of the flat gradient buffer (kernels accumulate there)."""
@@ -595,7 +637,7 @@ class TransformerModel(nn.Module):
             raise NotImplementedError("sequence length %d > 256 is not supported by the fused attention kernel" % S)
         p_drop, p_att = self._drop()
         seed, seed_word = self._next_seed()
-        self.refresh_operands()
+        ev_operands = self._start_operand_refresh()
         e = lambda *s, dt=_BF16: torch.empty(*s, dtype=dt, device=dev)
         seqlen = spec["lengths"].to(device=dev, dtype=torch.int32).contiguous()
         st = dict(spec=spec, seqlen=seqlen, seed=seed, seed_word=seed_word, p_drop=p_drop, p_att=p_att, B=B, T=T, R=R,
@@ -676,6 +718,9 @@ class TransformerModel(nn.Module):
         res, res_ln = h32, None  # what the next residual add reads: an fp32 tensor, or (pre-LN sum, LayerNorm recipe)
         recompute = os.environ.get("M3P_RES_LN", "1") != "0"  # 0: LayerNorm kernels also write an fp32 copy (A/B runs)
         for i in range(self.n_layers):
+            if i == 1 and ev_operands is not None:
+                torch.cuda.current_stream().wait_event(ev_operands)  # bf16 copies of layers 1.. and the heads are ready
+                ev_operands = None
             w = self._layer_views(i)
             s1, s2, sa = seed ^ (0x100 * (i + 1) + 1), seed ^ (0x100 * (i + 1) + 2), seed ^ (0x100 * (i + 1) + 3)
             qkv = e(M, 3 * d)
@@ -704,6 +749,10 @@ class TransformerModel(nn.Module):
                 st["layers"].append(dict(h=h, qkv=qkv, ctx=ctx, lse=lse, x1=x1, h1=h1, mean1=mean1, rstd1=rstd1, gp=gp,
                                          g=g, x2=x2, mean2=mean2, rstd2=rstd2, s1=s1, s2=s2, sa=sa))
             h = hn
+        if ev_operands is not None:
+            torch.cuda.current_stream().wait_event(ev_operands)
+        if self._emb16_event is not None:  # join the side stream here (free: the cast ended layers ago) so that a step
+            torch.cuda.current_stream().wait_event(self._emb16_event)  # without the MLM head leaves nothing unjoined
         return h, st
 
     def _encode_backward(self, st, dh, want_dximg, want_dtext):
@@ -786,7 +835,7 @@ class TransformerModel(nn.Module):
             ops.layernorm_bwd(dh, st["y_pre"], st["emb_mean"], st["emb_rstd"], self._w32("layer_norm_emb.weight"), dy_pre,
                               seqlen=seqlen, S=S, dy_drop_p=p_drop if (flags & L.M3P_EMB_DROP2) else 0.0,
                               dy_seed=st["seed"] ^ 0x2222, dgamma=self._g("layer_norm_emb.weight"),
-                              dbeta=self._g("layer_norm_emb.bias"))
+                              dbeta=self._g("layer_norm_emb.bias"), col_scratch=e(512 * 3 * d, dt=_F32))
         else:
             dy_pre = dh.to(_F32)  # fwd(cross_modal=True): image rows only, mask already applied upstream
         b = L.EmbedBwdArgs()
@@ -829,7 +878,7 @@ class TransformerModel(nn.Module):
                               self._w32("image_embeddings.LayerNorm.weight"), de, dy_drop_p=p_drop,
                               dy_seed=st["seed"] ^ 0x1111, dgamma=self._g("image_embeddings.LayerNorm.weight"),
                               dbeta=self._g("image_embeddings.LayerNorm.bias"),
-                              dbias=self._g("image_embeddings.image_embeddings.bias"))
+                              dbias=self._g("image_embeddings.image_embeddings.bias"), col_scratch=e(512 * 3 * d, dt=_F32))
             ops.colsum(de, self._g("image_embeddings.image_location_embeddings.bias"))
             ops.wgrad(de, st["ximg16"], self._g("image_embeddings.image_embeddings.weight"))
             ops.loc_wgrad(de, st["loc"], self._g("image_embeddings.image_location_embeddings.weight"), B, R, d)

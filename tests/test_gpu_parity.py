@@ -1033,6 +1033,23 @@ def test_gemm_fp32_residual_epilogue(m3p, m, n, k, masked):
     assert abs(kept - 0.8) < 0.02
 
 
+@pytest.mark.parametrize("n_groups,sample_n", [(16, 4), (2, 2), (1500, 4), (7, 9)])
+def test_relation_loss_kernel(m3p, n_groups, sample_n):
+    """m3p_relation_loss == CE over groups + BCEWithLogits against the one-hot positive (xtrainer.py:2359-2372),
+    value and gradient, with loss weights."""
+    from m3p_b200.train_step import relation_loss
+    g = torch.Generator(device="cuda").manual_seed(n_groups)
+    scores = (torch.randn(n_groups * sample_n, 1, device="cuda", generator=g) * 3).requires_grad_(True)
+    pos = torch.randint(0, sample_n, (n_groups,), device="cuda", generator=g)
+    loss = relation_loss(scores, pos, sample_n, 0.7, 1.3)
+    (loss * 2.0).backward()
+    s2 = scores.detach().clone().requires_grad_(True)
+    ref = 0.7 * F.cross_entropy(s2.view(-1, sample_n), pos) + 1.3 * F.binary_cross_entropy_with_logits(
+        s2.view(-1), F.one_hot(pos, sample_n).float().view(-1))
+    (ref * 2.0).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref)) and _rel(scores.grad, s2.grad) < 1e-5
+
+
 def test_cuda_graph_step_matches_eager_and_redraws_dropout(m3p):
     """GraphedStep: the captured step reproduces the eager gradients, accepts new inputs, and — because the
     dropout seeds live in a device word bumped inside the graph — draws new masks on every replay."""
