@@ -142,6 +142,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(bar_s, 1);
       mbar_init(bar_o, 1);
       fence_barrier_init();
+      // the operand loads only need the barriers: they fly during the TMEM allocation and the CTA-wide sync
+      mbar_arrive_expect_tx(bar_qk, 48 * 1024);
+      tma_load_3d(sQ, &tmap_q, bar_qk, h * ATT_DH, mt * 128, b);
+      tma_load_3d(sK, &tmap_kv, bar_qk, p.d + h * ATT_DH, 0, b);
+      mbar_arrive_expect_tx(bar_v, 32 * 1024);
+      tma_load_3d(sV, &tmap_kv, bar_v, 2 * p.d + h * ATT_DH, 0, b);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, 256);
@@ -157,11 +163,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (control) {
     // ================================ control warp ================================
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_qk, 48 * 1024);
-      tma_load_3d(sQ, &tmap_q, bar_qk, h * ATT_DH, mt * 128, b);
-      tma_load_3d(sK, &tmap_kv, bar_qk, p.d + h * ATT_DH, 0, b);
-      mbar_arrive_expect_tx(bar_v, 32 * 1024);
-      tma_load_3d(sV, &tmap_kv, bar_v, 2 * p.d + h * ATT_DH, 0, b);
       mbar_wait(bar_qk, 0);
       tc_fence_after();
       const uint32_t idesc = make_idesc_bf16(128, p.n_kv, 0, 0);
@@ -319,7 +320,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (threadIdx.x == 0) {
       tma_store_3d(&tmap_ctx, sV, h * ATT_DH, mt * 128, b);
       tma_store_commit();
-      tma_store_wait<0>();  // shared memory must outlive the bulk store that reads it
+      tma_store_wait_read<0>();  // shared memory must outlive the bulk store's READS (the writes drain after exit)
     }
   }
   tc_fence_before();
@@ -399,6 +400,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_init(bar_sd, 1);
       mbar_init(bar_g, 1);
       fence_barrier_init();
+      // Q, K, V, dO and (temporarily, in the P staging buffer) the forward output O: the loads only need the barrier,
+      // so they fly during the TMEM allocation and the CTA-wide sync
+      mbar_arrive_expect_tx(bar_ld, 5 * 32 * 1024);
+      tma_load_3d(sQ, &tmap_qkv, bar_ld, h * ATT_DH, 0, b);
+      tma_load_3d(sK, &tmap_qkv, bar_ld, p.d + h * ATT_DH, 0, b);
+      tma_load_3d(sV, &tmap_qkv, bar_ld, 2 * p.d + h * ATT_DH, 0, b);
+      tma_load_3d(sdO, &tmap_do, bar_ld, h * ATT_DH, 0, b);
+      tma_load_3d(sP, &tmap_o, bar_ld, h * ATT_DH, 0, b);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, 512);
@@ -440,13 +449,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       umma_commit(bar_sd);
     };
     if (lane == 0) {
-      // Q, K, V, dO and (temporarily, in the P staging buffer) the forward output O
-      mbar_arrive_expect_tx(bar_ld, 5 * 32 * 1024);
-      tma_load_3d(sQ, &tmap_qkv, bar_ld, h * ATT_DH, 0, b);
-      tma_load_3d(sK, &tmap_qkv, bar_ld, p.d + h * ATT_DH, 0, b);
-      tma_load_3d(sV, &tmap_qkv, bar_ld, 2 * p.d + h * ATT_DH, 0, b);
-      tma_load_3d(sdO, &tmap_do, bar_ld, h * ATT_DH, 0, b);
-      tma_load_3d(sP, &tmap_o, bar_ld, h * ATT_DH, 0, b);
       mbar_wait(bar_ld, 0);
       issue_s_dp(0, 0);
     }
@@ -651,7 +653,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     if (threadIdx.x == 0) {
       for (int i = 0; i < NT; ++i) tma_store_3d(&tmap_dqkv, sQ + i * TILE16K, h * ATT_DH, i * 128, b);
       tma_store_commit();
-      tma_store_wait<0>();  // shared memory must outlive the bulk stores that read it
+      tma_store_wait_read<0>();  // shared memory must outlive the bulk stores' READS (the writes drain after exit)
     }
   }
   tc_fence_before();

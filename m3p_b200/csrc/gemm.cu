@@ -48,6 +48,11 @@ constexpr uint32_t SLAB_BYTES = 64 * BLOCK_K * 2;  // one 64-wide MN slab of an 
 struct GemmKernelParams {
   int M, N, K;
   int num_n_tiles, num_m_tiles, m_fastest, split_k, num_units;
+  // Tail balancing: units [wide_units, num_units) are HALF-width tiles (BN / 2 columns).  When the last wave of full
+  // tiles would occupy at most half of the CTA pairs (N = 768: 171 tiles on 74 pairs = 2 waves + 23), those tiles are
+  // cut in two so the wave costs half a tile time (3 -> 2.5 tile times).  wide_units == num_units: uniform tiling.
+  int wide_units;
+  uint32_t idesc_half;
   int kblocks_total, kblocks_per_split;
   int a_mn, b_mn;
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
@@ -80,10 +85,22 @@ struct GemmKernelParams {
 // L2 by the others; the operand indexed by the slower dimension is re-read once per wave.  Making the short
 // dimension fast keeps the sharers of the LARGE operand together (FFN lin2 wgrad, 3 x 12 tiles: 214 -> ~134 MB of
 // DRAM reads per launch).
-__device__ __forceinline__ void decode_unit(const GemmKernelParams& p, int u, int& m_tile,
-                                            int& n_tile, int& ks) {
+// n0 / bn: first column and width of the unit's tile (bn = BN, or BN / 2 for the half-width tail units).
+template <int BN>
+__device__ __forceinline__ void decode_unit(const GemmKernelParams& p, int u, int& m_tile, int& n0, int& bn, int& ks) {
+  if (u >= p.wide_units) {
+    // half-width tail (host guarantees split_k == 1 and the N-fastest order): count in half-tile columns
+    const int g = 2 * p.wide_units + (u - p.wide_units);
+    const int per_row = 2 * p.num_n_tiles;
+    m_tile = g / per_row;
+    n0 = (g % per_row) * (BN / 2);
+    bn = BN / 2;
+    ks = 0;
+    return;
+  }
   ks = u % p.split_k;
   const int t = u / p.split_k;
+  int n_tile;
   if (p.m_fastest) {
     m_tile = t % p.num_m_tiles;
     n_tile = t / p.num_m_tiles;
@@ -91,6 +108,8 @@ __device__ __forceinline__ void decode_unit(const GemmKernelParams& p, int u, in
     n_tile = t % p.num_n_tiles;
     m_tile = t / p.num_n_tiles;
   }
+  n0 = n_tile * BN;
+  bn = BN;
 }
 
 // ---- epilogue math on one 16-column chunk held by one thread (one output row) -------------------
@@ -339,8 +358,9 @@ struct GemmCfg {
 template <int BN, int EPI, bool OUT_F32, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
-            const __grid_constant__ CUtensorMap tmap_aux, const GemmKernelParams p) {
+            const __grid_constant__ CUtensorMap tmap_bh, const __grid_constant__ CUtensorMap tmap_o,
+            const __grid_constant__ CUtensorMap tmap_o2, const __grid_constant__ CUtensorMap tmap_aux,
+            const GemmKernelParams p) {
   using Cfg = GemmCfg<BN, CTA2, EPI, OUT_F32>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NCTA = CTA2 ? 2 : 1;
@@ -369,6 +389,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp_idx == 0 && elect_one()) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (p.wide_units < p.num_units && !p.b_mn) prefetch_tmap(&tmap_bh);
     if (p.tma_store) {
       prefetch_tmap(&tmap_o);
       if constexpr (EPI == M3P_EPI_GELU) prefetch_tmap(&tmap_o2);
@@ -409,16 +430,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t phase = 0;
       for (int u = unit0; u < p.num_units; u += unit_stride) {
         GT_MARK();  // producer: tile start
-        int m_tile, n_tile, ks;
-        decode_unit(p, u, m_tile, n_tile, ks);
+        int m_tile, n_base, bn, ks;
+        decode_unit<BN>(p, u, m_tile, n_base, bn, ks);
+        const int bn_load = CTA2 ? bn / 2 : bn;  // B rows this CTA stages for this unit
         const int m0 = (m_tile * NCTA + (int)cta_rank) * BLOCK_M;
-        const int n0 = n_tile * BN + (int)cta_rank * Cfg::BN_LOAD;
+        const int n0 = n_base + (int)cta_rank * bn_load;
+        const uint32_t stage_tx = (Cfg::A_BYTES + static_cast<uint32_t>(bn_load) * BLOCK_K * 2) * NCTA;
         const int kb0 = ks * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           // the pair's bytes are all counted on the leader's barrier
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * NCTA);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           const int k0 = kb * BLOCK_K;
@@ -433,10 +456,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int s = 0; s < BLOCK_M / 64; ++s) load(sa + s * SLAB_BYTES, &tmap_a, m0 + s * 64, k0);
           }
           if (!p.b_mn) {
-            load(sb, &tmap_b, k0, n0);
+            load(sb, bn == BN ? &tmap_b : &tmap_bh, k0, n0);  // the half-width box is half as tall
           } else {
 #pragma unroll
-            for (int s = 0; s < Cfg::BN_LOAD / 64; ++s) load(sb + s * SLAB_BYTES, &tmap_b, n0 + s * 64, k0);
+            for (int s = 0; s < Cfg::BN_LOAD / 64; ++s)
+              if (s * 64 < bn_load) load(sb + s * SLAB_BYTES, &tmap_b, n0 + s * 64, k0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -456,8 +480,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint64_t bdesc_base = make_smem_desc(smem_u32(smem) + Cfg::A_BYTES, p.b_lbo, p.b_sbo);
       const uint64_t a_kstep4 = p.a_kstep >> 4, b_kstep4 = p.b_kstep >> 4;
       for (int u = unit0; u < p.num_units; u += unit_stride) {
-        int m_tile, n_tile, ks;
-        decode_unit(p, u, m_tile, n_tile, ks);
+        int m_tile, n_base, bn, ks;
+        decode_unit<BN>(p, u, m_tile, n_base, bn, ks);
+        const uint32_t idesc = bn == BN ? p.idesc : p.idesc_half;
         const int kb0 = ks * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
         GT_MARK();  // mma: tile start
@@ -476,8 +501,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = adesc0 + static_cast<uint64_t>(k) * a_kstep4;
             const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(k) * b_kstep4;
-            if constexpr (CTA2) umma_ss_2sm(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_ss(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CTA2) umma_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           // smem slot reusable (in both CTAs) once these MMAs retire
           if constexpr (CTA2) umma_commit_2sm(&empty_bar[stage], 3);
@@ -497,14 +522,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int ew = warp_idx - 4;
     const int q = warp_idx & 3;   // TMEM lane quarter this warp may access
     const int half = ew >> 2;     // which half of the tile's columns this warp drains
-    constexpr int NCH = BN / 2 / EW;  // 16-column chunks per warp per tile
     constexpr bool F32R = Cfg::F32R;  // fp32 aux + fp32 output through the ring (16 columns per 64-byte tile row)
     constexpr int GWC = F32R ? EW : GW;  // columns per staging group
-    constexpr int NG = BN / 2 / GWC;     // staging groups per warp per tile
+    constexpr int NG = BN / 2 / GWC;     // staging groups per warp per full-width tile (half of that for a half-width one)
     constexpr int CPG = GWC / EW;        // 16-column chunks per staging group
     constexpr bool HAS_AUX = epi_has_aux<EPI>();
     constexpr int RING = Cfg::RING;
-    const int cbase = half * (BN / 2);
     float* sbias = bias_smem + ew * (BN / 2) * (F32R ? 3 : 1);
     float* sgamma = sbias + BN / 2;   // F32R only
     float* sbeta = sgamma + BN / 2;
@@ -521,12 +544,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     long long ax_u = unit0;      // unit of the group the cursor points at
     int ax_g = 0, ax_slot = 0;   // its group index inside the tile and its ring slot
     int ax_col = 0, ax_row0 = 0; // first column of the tile's slice for this warp / first row of its sub-tile
+    int ax_ng = NG;              // staging groups of the cursor's tile
     auto ax_decode = [&]() {
       if (ax_u < p.num_units) {
-        int m_tile, n_tile, ks;
-        decode_unit(p, static_cast<int>(ax_u), m_tile, n_tile, ks);
-        ax_col = n_tile * BN + cbase;
+        int m_tile, n_base, bn, ks;
+        decode_unit<BN>(p, static_cast<int>(ax_u), m_tile, n_base, bn, ks);
+        ax_col = n_base + half * (bn / 2);
         ax_row0 = (m_tile * NCTA + (int)cta_rank) * BLOCK_M + q * 32;
+        ax_ng = bn / 2 / GWC;
       }
     };
     auto issue_aux = [&]() {  // lane 0: request the cursor's group, then advance the cursor
@@ -536,7 +561,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tma_load_2d(ring + ax_slot * STG_TILE, &tmap_aux, &my_aux_bar[ax_slot], col0, ax_row0);
       }
       if (++ax_slot == RING) ax_slot = 0;
-      if (++ax_g == NG) { ax_g = 0; ax_u += unit_stride; ax_decode(); }
+      if (++ax_g == ax_ng) { ax_g = 0; ax_u += unit_stride; ax_decode(); }
     };
     if constexpr (HAS_AUX) {
       if (use_tma && lane == 0) {
@@ -552,14 +577,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     GT_DECL
     for (int u = unit0; u < p.num_units; u += unit_stride) {
       GT_MARK();  // epi: tile start
-      int m_tile, n_tile, ks;
-      decode_unit(p, u, m_tile, n_tile, ks);
-      const int n0 = n_tile * BN;
+      int m_tile, n0, bn, ks;
+      decode_unit<BN>(p, u, m_tile, n0, bn, ks);
+      const int cbase = half * (bn / 2);  // this warp's half of the tile's columns
+      const int nch = bn / 2 / EW;        // 16-column chunks per warp for this tile
+      const int ng = bn / 2 / GWC;        // staging groups per warp for this tile
       const int row0 = (m_tile * NCTA + (int)cta_rank) * BLOCK_M + q * 32;  // first row of this warp's sub-tile
       const long long row = static_cast<long long>(row0) + lane;
       const bool row_ok = row < p.M;
       // stage this warp's bias slice (the global loads overlap the wait for the accumulator)
-      for (int c = lane * 4; c < BN / 2; c += 128) {
+      for (int c = lane * 4; c < bn / 2; c += 128) {
         const int col = n0 + cbase + c;
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias != nullptr) {
@@ -606,7 +633,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tmem_ld_32x32b_x16(t_base + cbase, acc[0]);
       if (use_tma) {
 #pragma unroll
-        for (int g = 0; g < NG; ++g, ++gg) {
+        for (int g = 0; g < NG; ++g) {
+          if (g >= ng) break;  // half-width tile
           const int b = gg % RING;
           const int gcol0 = n0 + cbase + g * GWC;
           const bool valid = gcol0 < p.N && row0 < p.M;
@@ -627,7 +655,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int ci = 0; ci < CPG; ++ci) {
             const int i = g * CPG + ci, ii = i & 1;
             tmem_ld_wait16(acc[ii]);
-            if (i + 1 < NCH) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
+            if (i + 1 < nch) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
             float v[EW], gq[EW], x[EW];
             if constexpr (F32R) {
               unstage_f32x16(slot, lane, x);
@@ -680,15 +708,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #ifdef M3P_GEMM_TRACE
           if (gg >= NG && gg < 2 * NG) GT_MARK();  // epi (2nd tile): store issued, next aux requested
 #endif
+          ++gg;
         }
       } else {
 #pragma unroll 1
-        for (int i0 = 0; i0 < NCH; i0 += 2) {
+        for (int i0 = 0; i0 < nch; i0 += 2) {
 #pragma unroll
           for (int ii = 0; ii < 2; ++ii) {
             const int i = i0 + ii;
             tmem_ld_wait16(acc[ii]);
-            if (i + 1 < NCH) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
+            if (i + 1 < nch) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
             const int col0 = n0 + cbase + i * EW;
             if (row_ok && col0 < p.N)
               epilogue_chunk_direct<EPI, OUT_F32>(p, acc[ii], sbias + i * EW, row, col0, min(EW, p.N - col0), seed_lo,
@@ -705,7 +734,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
-    if (lane == 0) tma_store_wait<0>();  // smem must outlive the bulk stores that read it
+    if (lane == 0) tma_store_wait_read<0>();  // smem must outlive the bulk stores' reads (the writes drain after exit)
 #ifdef M3P_GEMM_TRACE
     if (warp_idx == 4 && lane == 0) { GT_MARK(); GT_DUMP("epi "); }
 #endif
@@ -723,8 +752,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // host launcher
 // ---------------------------------------------------------------------------------------------
 template <int BN, int EPI, bool OUT_F32, bool CTA2>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
-                       const CUtensorMap& tx, const GemmKernelParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& to,
+                       const CUtensorMap& to2, const CUtensorMap& tx, const GemmKernelParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTA2, EPI, OUT_F32>;
   auto kfn = gemm_kernel<BN, EPI, OUT_F32, CTA2>;
   static bool attr_set = false;  // per instantiation
@@ -750,28 +779,29 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  M3P_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, ta, tb, to, to2, tx, p));
+  M3P_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, ta, tb, tbh, to, to2, tx, p));
   return M3P_OK;
 }
 
 template <int BN, bool CTA2>
-static int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
-                        const CUtensorMap& tx, const GemmKernelParams& p, int epi, bool out_f32, cudaStream_t s) {
+static int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& to,
+                        const CUtensorMap& to2, const CUtensorMap& tx, const GemmKernelParams& p, int epi, bool out_f32,
+                        cudaStream_t s) {
   if (out_f32) {
-    if (epi == M3P_EPI_DROP_RES) return launch_gemm<BN, M3P_EPI_DROP_RES, true, CTA2>(ta, tb, to, to2, tx, p, s);
+    if (epi == M3P_EPI_DROP_RES) return launch_gemm<BN, M3P_EPI_DROP_RES, true, CTA2>(ta, tb, tbh, to, to2, tx, p, s);
     if (epi != M3P_EPI_LINEAR) {
       set_last_error("m3p_gemm_bf16: fp32 output only with M3P_EPI_LINEAR or M3P_EPI_DROP_RES");
       return M3P_ERR_UNSUPPORTED;
     }
-    return launch_gemm<BN, M3P_EPI_LINEAR, true, CTA2>(ta, tb, to, to2, tx, p, s);
+    return launch_gemm<BN, M3P_EPI_LINEAR, true, CTA2>(ta, tb, tbh, to, to2, tx, p, s);
   }
   switch (epi) {
-    case M3P_EPI_LINEAR: return launch_gemm<BN, M3P_EPI_LINEAR, false, CTA2>(ta, tb, to, to2, tx, p, s);
-    case M3P_EPI_GELU: return launch_gemm<BN, M3P_EPI_GELU, false, CTA2>(ta, tb, to, to2, tx, p, s);
-    case M3P_EPI_DROP_RES: return launch_gemm<BN, M3P_EPI_DROP_RES, false, CTA2>(ta, tb, to, to2, tx, p, s);
-    case M3P_EPI_DGELU: return launch_gemm<BN, M3P_EPI_DGELU, false, CTA2>(ta, tb, to, to2, tx, p, s);
-    case M3P_EPI_TANH: return launch_gemm<BN, M3P_EPI_TANH, false, CTA2>(ta, tb, to, to2, tx, p, s);
-    case M3P_EPI_DTANH: return launch_gemm<BN, M3P_EPI_DTANH, false, CTA2>(ta, tb, to, to2, tx, p, s);
+    case M3P_EPI_LINEAR: return launch_gemm<BN, M3P_EPI_LINEAR, false, CTA2>(ta, tb, tbh, to, to2, tx, p, s);
+    case M3P_EPI_GELU: return launch_gemm<BN, M3P_EPI_GELU, false, CTA2>(ta, tb, tbh, to, to2, tx, p, s);
+    case M3P_EPI_DROP_RES: return launch_gemm<BN, M3P_EPI_DROP_RES, false, CTA2>(ta, tb, tbh, to, to2, tx, p, s);
+    case M3P_EPI_DGELU: return launch_gemm<BN, M3P_EPI_DGELU, false, CTA2>(ta, tb, tbh, to, to2, tx, p, s);
+    case M3P_EPI_TANH: return launch_gemm<BN, M3P_EPI_TANH, false, CTA2>(ta, tb, tbh, to, to2, tx, p, s);
+    case M3P_EPI_DTANH: return launch_gemm<BN, M3P_EPI_DTANH, false, CTA2>(ta, tb, tbh, to, to2, tx, p, s);
     default:
       set_last_error("m3p_gemm_bf16: unknown epilogue %d", epi);
       return M3P_ERR_INVALID_ARGUMENT;
@@ -792,6 +822,16 @@ static bool use_cta_pairs() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("M3P_GEMM_2CTA");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// M3P_GEMM_TAIL_BALANCE=0 keeps uniform tiles (A/B measurements)
+static bool use_tail_balance() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("M3P_GEMM_TAIL_BALANCE");
     v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
@@ -842,6 +882,17 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   const long long units = (long long)num_m_tiles * p.num_n_tiles * split;
   M3P_REQUIRE(units < (1ll << 31), "m3p_gemm_bf16: too many tiles");
   p.num_units = (int)units;
+  p.wide_units = p.num_units;
+  // Tail balancing (see GemmKernelParams::wide_units): full 256 x 256 tiles on CTA pairs, N-fastest order, no K split,
+  // and a last wave that would leave at least half of the pairs idle -> its tiles are issued as two half-width units.
+  if (cta2 && BN == 256 && split == 1 && !p.m_fastest && p.N % BN == 0 && use_tail_balance()) {
+    const int workers = sm_count() / 2;
+    const int rem = p.num_units % workers;
+    if (p.num_units > workers && rem > 0 && 2 * rem <= workers) {
+      p.wide_units = p.num_units - rem;
+      p.num_units = p.wide_units + 2 * rem;
+    }
+  }
   p.a_mn = a->a_mn_major ? 1 : 0;
   p.b_mn = a->b_mn_major ? 1 : 0;
   // descriptor constants (see ptx.cuh make_smem_desc)
@@ -858,6 +909,7 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
   if (b_sbo >= 0) p.b_sbo = b_sbo;
   if (b_kstep >= 0) p.b_kstep = b_kstep;
   p.idesc = make_idesc_bf16(tile_m, BN, p.a_mn, p.b_mn);
+  p.idesc_half = make_idesc_bf16(tile_m, BN / 2, p.a_mn, p.b_mn);
   p.alpha = a->alpha;
   p.bias = a->bias;
   p.out = a->out; p.ldo = a->ldo;
@@ -896,6 +948,11 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
                                      cta2 ? BN / 2 : BN);
   else         rc = get_tmap_2d_bf16(&tb, a->b, (uint64_t)a->n, (uint64_t)a->k, (uint64_t)a->ldb, 64, BLOCK_K);
   if (rc) return rc;
+  CUtensorMap tbh = tb;  // K-major B box of a half-width unit (an MN-major B just loads half as many 64-wide slabs)
+  if (p.wide_units < p.num_units && !p.b_mn) {
+    rc = get_tmap_2d_bf16(&tbh, a->b, (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, BLOCK_K, BN / 4);
+    if (rc) return rc;
+  }
 
   // bf16 outputs (and the aux operand): [32 rows][32 cols] SWIZZLE_64B boxes for the TMA epilogue
   CUtensorMap to = ta, to2 = ta, tx = ta;
@@ -922,11 +979,11 @@ int gemm_impl(const m3p_gemm_args* a, int a_lbo, int a_sbo, int a_kstep, int b_l
     return M3P_ERR_UNSUPPORTED;
   }
   if (cta2) {
-    if (BN == 256) return dispatch_epi<256, true>(ta, tb, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
-    return dispatch_epi<128, true>(ta, tb, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
+    if (BN == 256) return dispatch_epi<256, true>(ta, tb, tbh, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
+    return dispatch_epi<128, true>(ta, tb, tbh, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
   }
-  if (BN == 256) return dispatch_epi<256, false>(ta, tb, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
-  return dispatch_epi<128, false>(ta, tb, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
+  if (BN == 256) return dispatch_epi<256, false>(ta, tb, tbh, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
+  return dispatch_epi<128, false>(ta, tb, tbh, to, to2, tx, p, a->epilogue, a->out_f32 != 0, stream);
 }
 
 }  // namespace m3p

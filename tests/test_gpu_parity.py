@@ -999,6 +999,47 @@ def test_gemm_fused_epilogues(m3p):
     assert _rel(o, torch.tanh(0.1 * (ref - bias) + bias)) < KERNEL_TOL
 
 
+@pytest.mark.parametrize("m,n,k", [(6600, 768, 192), (1792, 3072, 128), (14592, 768, 3072)])
+def test_gemm_tail_balanced_half_width_tiles(m3p, m, n, k):
+    """Shapes whose last wave of 256 x 256 tiles would leave most CTA pairs idle end in half-width (256 x 128) units
+    (`GemmKernelParams::wide_units`): every epilogue and both B layouts (forward K-major weights, dgrad MN-major
+    weights) must give the same numbers as on uniform tiles — checked against torch, ragged M included, twice in a
+    row (ring / phase state across mixed tile widths)."""
+    from m3p_b200 import lib as L, ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = (torch.randn(m, k, device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn(n, k, device="cuda", generator=g) * 0.1).bfloat16()
+    Bt = B.t().contiguous()  # [k][n]: dgrad reads the weight of the forward GEMM un-transposed
+    bias = torch.randn(n, device="cuda", generator=g)
+    aux16 = torch.randn(m, n, device="cuda", generator=g).bfloat16()
+    aux32 = torch.randn(m, n, device="cuda", generator=g)
+    ref = A.float() @ B.float().t()
+    for rep in range(2):
+        for b_mn, Bop in ((False, B), (True, Bt)):
+            o = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+            ops.gemm(A, Bop, m, n, k, o, b_mn=b_mn, bias=bias)
+            assert _rel(o, (ref + bias).bfloat16()) < 1e-3, (rep, b_mn)
+            cs = torch.zeros(n, device="cuda")
+            ops.gemm(A, Bop, m, n, k, o, b_mn=b_mn, epi=L.M3P_EPI_DGELU, aux=aux16, colsum=cs)
+            assert _rel(o, (ref * aux16.float()).bfloat16()) < 1e-3, (rep, b_mn)
+            assert float((cs - o.float().sum(0)).abs().max()) < 1e-3 * float(o.float().sum(0).abs().max())
+            o32 = torch.empty(m, n, device="cuda")
+            ops.gemm(A, Bop, m, n, k, o32, b_mn=b_mn, bias=bias, epi=L.M3P_EPI_DROP_RES, aux=aux32, out_f32=True)
+            assert _rel(o32, ref + bias + aux32) < 1e-5, (rep, b_mn)
+        o, o2 = torch.empty(m, n, device="cuda", dtype=torch.bfloat16), torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(A, B, m, n, k, o, bias=bias, epi=L.M3P_EPI_GELU, out2=o2)
+        u = ref + bias
+        cdf = 0.5 * (1 + torch.erf(u / 2 ** 0.5))
+        assert _rel(o2, (u * cdf).bfloat16()) < 2e-3 and _rel(o, cdf + u * torch.exp(-0.5 * u * u) / (2 * 3.141592653589793) ** 0.5) < 2e-3
+    # the dropout mask is a function of the element index, not of the tiling: same seed -> same mask as the backward's
+    o32a, o32b = torch.empty(m, n, device="cuda"), torch.empty(m, n, device="cuda")
+    ops.gemm(A, B, m, n, k, o32a, bias=bias, epi=L.M3P_EPI_DROP_RES, aux=aux32, out_f32=True, drop_p=0.3, seed=21)
+    ops.gemm(A, Bt, m, n, k, o32b, b_mn=True, bias=bias, epi=L.M3P_EPI_DROP_RES, aux=aux32, out_f32=True, drop_p=0.3, seed=21)
+    assert torch.equal(o32a, o32b)
+    kept = ((o32a - aux32).abs() > 1e-6).float().mean().item()
+    assert abs(kept - 0.7) < 0.02
+
+
 @pytest.mark.parametrize("m,n,k,masked", [(300, 392, 200, True), (14592, 768, 768, True), (7296, 768, 3072, False)])
 def test_gemm_fp32_residual_epilogue(m3p, m, n, k, masked):
     """M3P_EPI_DROP_RES with out_f32 / aux_f32: out = aux + (A B^T + bias) in fp32 — the encoder's residual stream —
