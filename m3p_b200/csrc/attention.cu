@@ -348,22 +348,67 @@ __device__ __forceinline__ void store_acc32(__nv_bfloat16* dst, const uint32_t* 
                        pack_bf16x2(__uint_as_float(acc[8 * g + 6]) * mul, __uint_as_float(acc[8 * g + 7]) * mul));
 }
 
-// Warp roles (288 threads): warps 0-7 do the softmax / dS math and the epilogues (two threads per
-// query row, 64 keys each); warp 8 is the control warp — one lane issues every TMA load and every
-// tcgen05.mma, so the math warps never stall behind MMA issue and the tensor pipe works on block n's
-// dV / dK / dQ while the math warps are already on block n+1.  Hand-offs:
+// Warp roles (MW * 32 + 32 threads, MW = 8 or 16 math warps): the math warps do the softmax / dS math and the
+// epilogues — MW / 4 threads per query row, each owning 128 / (MW / 4) keys of a block; the last warp is the control
+// warp — one lane issues every TMA load and every tcgen05.mma, so the math warps never stall behind MMA issue and the
+// tensor pipe works on block n's dV / dK / dQ while the math warps are already on block n+1.  Hand-offs:
 //   bar_sd (mbarrier, tcgen05.commit)  control -> math : S and dP of the block are in TMEM
 //   named barrier 1 (math arrive, control sync)        : S / dP have been read out of TMEM
 //   named barrier 2 (math arrive, control sync)        : P / dS of the block are in shared memory
 //   bar_g  (mbarrier, tcgen05.commit)  control -> math : the block's dV / dK / dQ MMAs have retired
-constexpr int BWD_MATH_THREADS = 256;
-constexpr int BWD_THREADS = BWD_MATH_THREADS + 32;
+// MW = 8 is what runs: with 16 math warps (four per scheduler, 96 registers per thread) the block math — ~10 instructions
+// per score element, half of them on the half-rate integer pipe — was NOT faster (pipe-throughput-bound, not latency-
+// bound) and the kernel lost 10 % to spills and the wider barriers.
 constexpr uint32_t NB_TMEM_FREE = 1, NB_SMEM_READY = 2, NB_MATH = 3;
 
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+// P and dS of one 32-key chunk (row q, keys key0 .. key0 + 31) from the raw scores / dP values, packed to bf16 pairs
+__device__ __forceinline__ void bwd_chunk_math(const AttnKernelParams& p, const uint32_t* sacc, const uint32_t* dacc,
+                                               float lse2, float delta, int key0, int L, int bh, int q, uint32_t seed_lo,
+                                               uint32_t seed_hi, uint32_t* ppk, uint32_t* dpk) {
+  if (key0 >= L) {
+#pragma unroll
+    for (int g = 0; g < 16; ++g) { ppk[g] = 0u; dpk[g] = 0u; }
+    return;
+  }
+  float pd[32];
+  // P (normalised: the forward's log2-sum-exp is subtracted inside the exponent)
+#pragma unroll
+  for (int jj = 0; jj < 32; ++jj) pd[jj] = ex2(fmaf(__uint_as_float(sacc[jj]), p.scale_log2, -lse2));
+  if (key0 + 32 > L) {  // the one chunk that straddles the key length
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) pd[jj] = (key0 + jj < L) ? pd[jj] : 0.f;
+  }
+  if (p.thr16 != 0) {
+    uint32_t lcg = drop_hash(attn_drop_base(bh, q, key0) >> 1, seed_lo, seed_hi);
+#pragma unroll
+    for (int jp = 0; jp < 16; ++jp) {
+      const uint32_t hsh = attn_drop_next(lcg);
+      const float k0 = ((hsh & 0xffffu) >= p.thr16) ? p.drop_scale : 0.f;
+      const float k1 = ((hsh >> 16) >= p.thr16) ? p.drop_scale : 0.f;
+      dpk[jp] = pack_bf16x2(pd[2 * jp] * fmaf(__uint_as_float(dacc[2 * jp]), k0, -delta),
+                            pd[2 * jp + 1] * fmaf(__uint_as_float(dacc[2 * jp + 1]), k1, -delta));
+      ppk[jp] = pack_bf16x2(pd[2 * jp] * k0, pd[2 * jp + 1] * k1);
+    }
+  } else {
+#pragma unroll
+    for (int jp = 0; jp < 16; ++jp) {
+      dpk[jp] = pack_bf16x2(pd[2 * jp] * (__uint_as_float(dacc[2 * jp]) - delta),
+                            pd[2 * jp + 1] * (__uint_as_float(dacc[2 * jp + 1]) - delta));
+      ppk[jp] = pack_bf16x2(pd[2 * jp], pd[2 * jp + 1]);
+    }
+  }
+}
+
+template <int MW>
+__global__ void __launch_bounds__(MW * 32 + 32, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_dqkv,
                 const AttnKernelParams p) {
+  constexpr int MATH_T = MW * 32;       // math threads
+  constexpr int THREADS = MATH_T + 32;  // + control warp
+  constexpr int CG = MW / 4;            // column groups: threads per query row
+  constexpr int NC = 4 / CG;            // 32-key chunks per thread per 128-key block (2 or 1)
+  constexpr int OC = ATT_DH / CG;       // columns of a [128][64] gradient tile per thread (32 or 16)
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment as an OFFSET from the __shared__ array, so every derived pointer keeps its shared-memory
   // provenance and the compiler emits LDS / STS instead of generic LD / ST
@@ -388,7 +433,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   const int h = blockIdx.x % p.H;
   const int b = blockIdx.x / p.H;
   const int bh = blockIdx.x;
-  const bool control = warp == 8;
+  const bool control = warp == MW;
 
   if (control) {
     if (elect_one()) {
@@ -455,10 +500,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     __syncwarp();
     for (int n = 0; n < nblocks; ++n) {
       const int j = n / NT, i = n % NT;
-      named_bar_sync(NB_TMEM_FREE, BWD_THREADS);
+      named_bar_sync(NB_TMEM_FREE, THREADS);
       if (lane == 0 && n + 1 < nblocks) issue_s_dp((n + 1) % NT, (n + 1) / NT);
       __syncwarp();
-      named_bar_sync(NB_SMEM_READY, BWD_THREADS);
+      named_bar_sync(NB_SMEM_READY, THREADS);
       if (lane == 0) {
         tc_fence_after();
         const uint64_t doa = dOm + i * T16, qa = dQm + i * T16, ka = dKm + j * T16;
@@ -479,28 +524,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     }
   } else {
     // ================================ math warps ================================
-    const int w4 = warp & 3, half = warp >> 2;
+    const int t = threadIdx.x;
+    const int w4 = warp & 3, cg = warp >> 2;  // TMEM lane quarter (rows); column group inside a block / gradient tile
     const int row = w4 * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(w4 * 32) << 16);
     uint32_t seed_lo = p.seed_lo, seed_hi = p.seed_hi;
     if (p.thr16 != 0) mix_seed(p.seed_mix, seed_lo, seed_hi);
-    {
-      const int r = threadIdx.x;
-      s_lse[r] = (r < p.S) ? p.lse[static_cast<long long>(bh) * p.S + r] : INFINITY;  // phantom rows: exp2(-inf) = 0
-    }
+    if (t < ATT_MAX_S)
+      s_lse[t] = (t < p.S) ? p.lse[static_cast<long long>(bh) * p.S + t] : INFINITY;  // phantom rows: exp2(-inf) = 0
     TRACE_MARK();  // setup
     mbar_wait(bar_ld, 0);
     __syncwarp();
     TRACE_MARK();  // loads landed
-    // ---- delta = rowsum(dO * O) from the TMA-staged (128B-swizzled) tiles: one thread per query row ----
+    // ---- delta = rowsum(dO * O) from the TMA-staged (128B-swizzled) tiles: MATH_T / 256 threads per query row ----
     {
-      const int r = threadIdx.x;
+      constexpr int TPR = MATH_T / ATT_MAX_S;  // 1 or 2
+      const int r = t / TPR, part = t % TPR;
       const uint8_t* dob = sdO + (r >> 7) * TILE16K;
       const uint8_t* ob = sP + (r >> 7) * TILE16K;
       float dl0 = 0.f, dl1 = 0.f;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint32_t off = swz_off(r & 127, g);
+      for (int g = 0; g < 8 / TPR; ++g) {
+        const uint32_t off = swz_off(r & 127, part * (8 / TPR) + g);
         const uint4 a = *reinterpret_cast<const uint4*>(dob + off);
         const uint4 o = *reinterpret_cast<const uint4*>(ob + off);
         dl0 = fmaf(bf16_lo(a.x), bf16_lo(o.x), dl0); dl1 = fmaf(bf16_hi(a.x), bf16_hi(o.x), dl1);
@@ -508,9 +553,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         dl0 = fmaf(bf16_lo(a.z), bf16_lo(o.z), dl0); dl1 = fmaf(bf16_hi(a.z), bf16_hi(o.z), dl1);
         dl0 = fmaf(bf16_lo(a.w), bf16_lo(o.w), dl0); dl1 = fmaf(bf16_hi(a.w), bf16_hi(o.w), dl1);
       }
-      s_delta[r] = dl0 + dl1;
+      float dl = dl0 + dl1;
+      if constexpr (TPR == 2) dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+      if (part == 0) s_delta[r] = dl;
     }
-    named_bar_sync(NB_MATH, BWD_MATH_THREADS);  // s_delta / s_lse visible; O consumed before P overwrites it
+    named_bar_sync(NB_MATH, MATH_T);  // s_delta / s_lse visible; O consumed before P overwrites it
     TRACE_MARK();  // delta
     uint32_t ph_sd = 0, ph_g = 0;
     int g_pending = 0, epi_j = -1;
@@ -518,25 +565,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     // row-per-thread 16-byte global store costs 32 LSU cycles per warp instruction).  Staging space: the K / V
     // tiles of a finished key tile, and at the very end the Q tiles — all dead once the MMAs that read them
     // have retired.  The softmax scale is applied here, not per element.
-    auto stage32 = [&](uint8_t* tile, const uint32_t* acc, float mul) {
+    auto stage_cols = [&](uint8_t* tile, const uint32_t* acc, float mul) {  // this thread's OC of the tile's 64 columns
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        *reinterpret_cast<uint4*>(tile + swz_off(row, half * 4 + g)) =
+      for (int g = 0; g < OC / 8; ++g)
+        *reinterpret_cast<uint4*>(tile + swz_off(row, cg * (OC / 8) + g)) =
             make_uint4(pack_bf16x2(__uint_as_float(acc[8 * g + 0]) * mul, __uint_as_float(acc[8 * g + 1]) * mul),
                        pack_bf16x2(__uint_as_float(acc[8 * g + 2]) * mul, __uint_as_float(acc[8 * g + 3]) * mul),
                        pack_bf16x2(__uint_as_float(acc[8 * g + 4]) * mul, __uint_as_float(acc[8 * g + 5]) * mul),
                        pack_bf16x2(__uint_as_float(acc[8 * g + 6]) * mul, __uint_as_float(acc[8 * g + 7]) * mul));
     };
+    auto drain_tile = [&](uint32_t tcol, uint8_t* tile, float mul) {  // TMEM [128][64] fp32 -> bf16 staging tile
+      uint32_t a[OC];
+      if constexpr (OC == 32) {
+        tmem_ld_32x32b_x32(t_lane + tcol + cg * OC, a);
+        tmem_ld_wait32(a);
+      } else {
+        tmem_ld_32x32b_x16(t_lane + tcol + cg * OC, a);
+        tmem_ld_wait16(a);
+      }
+      stage_cols(tile, a, mul);
+    };
     auto store_dk_dv = [&](int j) {
-      uint32_t a[32], v[32];
-      tmem_ld_32x32b_x32(t_lane + TM_DK + half * 32, a);
-      tmem_ld_32x32b_x32(t_lane + TM_DV + half * 32, v);
-      tmem_ld_wait();
-      stage32(sK + j * TILE16K, a, p.scale);
-      stage32(sV + j * TILE16K, v, 1.0f);
+      drain_tile(TM_DK, sK + j * TILE16K, p.scale);
+      drain_tile(TM_DV, sV + j * TILE16K, 1.0f);
       fence_proxy_async_smem();
-      named_bar_sync(NB_MATH, BWD_MATH_THREADS);
-      if (threadIdx.x == 0) {
+      named_bar_sync(NB_MATH, MATH_T);
+      if (t == 0) {
         tma_store_3d(&tmap_dqkv, sK + j * TILE16K, p.d + h * ATT_DH, j * 128, b);
         tma_store_3d(&tmap_dqkv, sV + j * TILE16K, 2 * p.d + h * ATT_DH, j * 128, b);
         tma_store_commit();
@@ -550,58 +604,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       tc_fence_after();
       TRACE_MARK();  // S, dP ready
 
-      // ---- P and dS for this thread's row x 64 keys, kept packed in registers ----
+      // ---- P and dS for this thread's row x (128 / CG) keys, kept packed in registers ----
       const int q = i * 128 + row;
       const float lse2 = s_lse[q], delta = s_delta[q];
-      uint32_t ppk[2][16], dpk[2][16];
+      uint32_t ppk[NC][16], dpk[NC][16];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int col0 = half * 64 + c * 32;  // column inside the 128-key tile
-        const int key0 = j * 128 + col0;
+      for (int c = 0; c < NC; ++c) {
+        const int col0 = (cg * NC + c) * 32;  // column inside the 128-key tile
         uint32_t sacc[32], dacc[32];
         tmem_ld_32x32b_x32(t_lane + TM_S + col0, sacc);
         tmem_ld_32x32b_x32(t_lane + TM_DP + col0, dacc);
-        tmem_ld_wait();
-        if (c == 1) {
+        tmem_ld_wait32(sacc);
+        tmem_ld_wait32(dacc);
+        if (c == NC - 1) {
           // everything this thread needs from S / dP is in registers: the control warp may start the
           // next block's score MMAs while this chunk's math runs
           tc_fence_before();
-          named_bar_arrive(NB_TMEM_FREE, BWD_THREADS);
+          named_bar_arrive(NB_TMEM_FREE, THREADS);
         }
-        float pd[32], ds[32];
-        if (key0 >= L) {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) { pd[jj] = 0.f; ds[jj] = 0.f; }
-        } else {
-          // P (normalised: the forward's log2-sum-exp is subtracted inside the exponent)
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) pd[jj] = ex2(fmaf(__uint_as_float(sacc[jj]), p.scale_log2, -lse2));
-          if (key0 + 32 > L) {  // the one chunk that straddles the key length
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) pd[jj] = (key0 + jj < L) ? pd[jj] : 0.f;
-          }
-          if (p.thr16 != 0) {
-            uint32_t lcg = drop_hash(attn_drop_base(bh, q, key0) >> 1, seed_lo, seed_hi);
-#pragma unroll
-            for (int jp = 0; jp < 16; ++jp) {
-              const uint32_t hsh = attn_drop_next(lcg);
-              const float k0 = ((hsh & 0xffffu) >= p.thr16) ? p.drop_scale : 0.f;
-              const float k1 = ((hsh >> 16) >= p.thr16) ? p.drop_scale : 0.f;
-              ds[2 * jp] = pd[2 * jp] * fmaf(__uint_as_float(dacc[2 * jp]), k0, -delta);
-              ds[2 * jp + 1] = pd[2 * jp + 1] * fmaf(__uint_as_float(dacc[2 * jp + 1]), k1, -delta);
-              pd[2 * jp] *= k0;
-              pd[2 * jp + 1] *= k1;
-            }
-          } else {
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) ds[jj] = pd[jj] * (__uint_as_float(dacc[jj]) - delta);
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < 16; ++g) {
-          ppk[c][g] = pack_bf16x2(pd[2 * g], pd[2 * g + 1]);
-          dpk[c][g] = pack_bf16x2(ds[2 * g], ds[2 * g + 1]);
-        }
+        bwd_chunk_math(p, sacc, dacc, lse2, delta, j * 128 + col0, L, bh, q, seed_lo, seed_hi, ppk[c], dpk[c]);
       }
       TRACE_MARK();  // softmax / dS math
       // the previous block's dV/dK/dQ MMAs still read sP / sdS: wait before overwriting them.  If that block
@@ -620,20 +641,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           tc_fence_before();
         }
       }
-      {
-        uint8_t* pblk = sP + half * TILE16K;
-        uint8_t* dblk = sdS + half * TILE16K;
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+      for (int c = 0; c < NC; ++c) {
+        const int col0 = (cg * NC + c) * 32;
+        uint8_t* pblk = sP + (col0 >> 6) * TILE16K;   // 64-key k-block of the staged P / dS
+        uint8_t* dblk = sdS + (col0 >> 6) * TILE16K;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t off = swz_off(row, c * 4 + g);
-            *reinterpret_cast<uint4*>(pblk + off) = make_uint4(ppk[c][4 * g], ppk[c][4 * g + 1], ppk[c][4 * g + 2], ppk[c][4 * g + 3]);
-            *reinterpret_cast<uint4*>(dblk + off) = make_uint4(dpk[c][4 * g], dpk[c][4 * g + 1], dpk[c][4 * g + 2], dpk[c][4 * g + 3]);
-          }
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t off = swz_off(row, ((col0 & 63) >> 3) + g);
+          *reinterpret_cast<uint4*>(pblk + off) = make_uint4(ppk[c][4 * g], ppk[c][4 * g + 1], ppk[c][4 * g + 2], ppk[c][4 * g + 3]);
+          *reinterpret_cast<uint4*>(dblk + off) = make_uint4(dpk[c][4 * g], dpk[c][4 * g + 1], dpk[c][4 * g + 2], dpk[c][4 * g + 3]);
+        }
       }
       fence_proxy_async_smem();
-      named_bar_arrive(NB_SMEM_READY, BWD_THREADS);
+      named_bar_arrive(NB_SMEM_READY, THREADS);
       g_pending = 1;
       if (i == NT - 1) epi_j = j;  // dK_j / dV_j complete once this block's MMAs retire
     }
@@ -642,15 +663,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     __syncwarp();
     tc_fence_after();
     store_dk_dv(epi_j);
-    for (int i = 0; i < NT; ++i) {
-      uint32_t a[32];
-      tmem_ld_32x32b_x32(t_lane + TM_DQ + i * ATT_DH + half * 32, a);
-      tmem_ld_wait();
-      stage32(sQ + i * TILE16K, a, p.scale);
-    }
+    for (int i = 0; i < NT; ++i) drain_tile(TM_DQ + i * ATT_DH, sQ + i * TILE16K, p.scale);
     fence_proxy_async_smem();
-    named_bar_sync(NB_MATH, BWD_MATH_THREADS);
-    if (threadIdx.x == 0) {
+    named_bar_sync(NB_MATH, MATH_T);
+    if (t == 0) {
       for (int i = 0; i < NT; ++i) tma_store_3d(&tmap_dqkv, sQ + i * TILE16K, h * ATT_DH, i * 128, b);
       tma_store_commit();
       tma_store_wait_read<0>();  // shared memory must outlive the bulk stores' READS (the writes drain after exit)
@@ -734,12 +750,15 @@ extern "C" int m3p_attention_bwd(const m3p_attn_args* a, m3p_stream_t stream_) {
   if (rc) return rc;
   rc = get_tmap_3d_bf16(&tdq, a->dqkv, d3, (uint64_t)p.S, (uint64_t)p.B, d3, d3 * p.S, ATT_DH, 128, 1);
   if (rc) return rc;
+  // 8 math warps: the 16-warp instantiation (four threads per query row, 96 registers) was measured slower
+  // (105 vs 95 us per launch at B = 64: the block math is bound by pipe throughput, not by dependent-issue latency)
+  constexpr int MW = 8;
   static bool attr_set = false;
   if (!attr_set) {
-    M3P_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
+    M3P_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES));
     attr_set = true;
   }
-  attn_bwd_kernel<<<p.B * p.H, BWD_THREADS, BWD_SMEM_BYTES, stream>>>(tqkv, tdo, to, tdq, p);
+  attn_bwd_kernel<MW><<<p.B * p.H, MW * 32 + 32, BWD_SMEM_BYTES, stream>>>(tqkv, tdo, to, tdq, p);
   M3P_CUDA_OK(cudaGetLastError());
   return M3P_OK;
 }
@@ -748,8 +767,8 @@ extern "C" int m3p_attention_bwd(const m3p_attn_args* a, m3p_stream_t stream_) {
 extern "C" __attribute__((visibility("default"))) int m3p_debug_attn_occupancy(int bwd) {
   int n = -1;
   if (bwd) {
-    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_bwd_kernel, BWD_THREADS, BWD_SMEM_BYTES);
+    cudaFuncSetAttribute(attn_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_bwd_kernel<8>, 8 * 32 + 32, BWD_SMEM_BYTES);
   } else {
     cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM_BYTES);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_fwd_kernel, FWD_THREADS, FWD_SMEM_BYTES);
