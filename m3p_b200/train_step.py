@@ -8,6 +8,8 @@ Batches are dicts shaped like `retrieval_pretrain_collate` output (xtrainer.py:9
   x_labels (T,B) int64 (-1 = not masked), obj_labels (B,R) int64 (-1 = not masked),
   ori_feats (B,R,2048) fp32, pos_labels (B/sample_n,) int64.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -341,7 +343,11 @@ class GraphedStep:
         n0 = ops.LAUNCHES
         # after_backward may enqueue NCCL collectives (ddp.GradReducer.finish): they are captured like any other
         # kernel; pass capture_error_mode="thread_local" then, so NCCL's watchdog thread may keep polling events
-        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
+        # The activation-gradient chain is captured on a HIGH-priority stream and the parameter-gradient work of
+        # `_SideQueue` on a default-priority one: when both have thread blocks pending, an SM that frees up goes to the
+        # chain, and the weight-gradient GEMMs fill what the chain leaves idle (kernel nodes keep their stream's priority).
+        hi = torch.cuda.Stream(priority=-1) if os.environ.get("M3P_CHAIN_PRIORITY", "1") != "0" else None
+        with torch.cuda.graph(self.graph, stream=hi, capture_error_mode=capture_error_mode):
             self.loss = self._eager()
         self.launches_per_step = ops.LAUNCHES - n0
 
