@@ -879,13 +879,18 @@ class TransformerModel(nn.Module):
                               dy_seed=st["seed"] ^ 0x1111, dgamma=self._g("image_embeddings.LayerNorm.weight"),
                               dbeta=self._g("image_embeddings.LayerNorm.bias"),
                               dbias=self._g("image_embeddings.image_embeddings.bias"), col_scratch=e(512 * 3 * d, dt=_F32))
-            ops.colsum(de, self._g("image_embeddings.image_location_embeddings.bias"))
+            # the three parameter gradients that hang off `de` are independent: the location-embedding ones (two
+            # small HBM-bound kernels) run on the side stream underneath the projection's weight-gradient GEMM
+            sq.fork()
+            sq.run(lambda: ops.colsum(de, self._g("image_embeddings.image_location_embeddings.bias")))
+            sq.run(lambda: ops.loc_wgrad(de, st["loc"], self._g("image_embeddings.image_location_embeddings.weight"), B, R, d))
             ops.wgrad(de, st["ximg16"], self._g("image_embeddings.image_embeddings.weight"))
-            ops.loc_wgrad(de, st["loc"], self._g("image_embeddings.image_location_embeddings.weight"), B, R, d)
             if want_dximg:
                 dxi = e(B * R, FEAT_DIM)
                 ops.dgrad(de, self._w16("image_embeddings.image_embeddings.weight"), dxi)
                 d_ximg = dxi.view(B, R, FEAT_DIM).transpose(0, 1).to(_F32)
+            sq.close("embed_img", None, (de,))
+            sq.join_all()
         if hook is not None:
             hook("embed", *self._segments["embed"])
         return d_ximg, d_text
@@ -923,7 +928,7 @@ class _SideQueue:
             if ev is not None:
                 self.main.wait_event(ev)
             del keep
-            if self.hook is not None:
+            if self.hook is not None and seg is not None:  # seg None: a group with no gradient segment of its own
                 self.hook(name, *seg)
 
     def close(self, name, seg, keep):
