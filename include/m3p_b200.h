@@ -16,6 +16,9 @@
  *     and ACCUMULATED (+=) into caller-zeroed buffers.
  *   - token rows are batch-major: row = b * S + s (the reference's (bs, slen, dim) tensor,
  *     transformer.py:929-943).
+ *   - threading: one host thread per process drives one GPU (the one-process-per-GPU model of the path).  Entry points
+ *     may be called from different threads, but the seed word registered by m3p_set_seed_mix(), the library-owned scratch
+ *     buffer and the tensor-map cache are PROCESS-global and unsynchronised: concurrent callers must serialise themselves.
  */
 #ifndef M3P_B200_H_
 #define M3P_B200_H_
