@@ -229,7 +229,8 @@ M3P_API int m3p_layernorm_bwd(const m3p_ln_bwd_args* args, m3p_stream_t stream);
 M3P_API int m3p_layernorm_bwd_rows(const m3p_ln_bwd_args* args, m3p_stream_t stream);
 M3P_API int m3p_layernorm_bwd_cols(const m3p_ln_bwd_args* args, m3p_stream_t stream);
 
-/* out[j] += sum_rows x[row][j]   (bias gradients of q/k/v and lin1: autograd of :178-181,223) */
+/* out[j] += sum_rows x[row][j], j < n   (bias gradients of q/k/v, lin1 and the MLM projection: autograd of
+ * :178-181,223,112).  ld a multiple of 8 that covers n rounded up to 8 (n itself may be ragged, e.g. V = 250 002). */
 M3P_API int m3p_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int64_t n, m3p_stream_t stream);
 
 /* out = bf16(scale * in): refreshes the bf16 tensor-core copies of the fp32 master parameters. */

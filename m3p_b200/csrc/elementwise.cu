@@ -1377,8 +1377,11 @@ extern "C" int m3p_layernorm_bwd_cols(const m3p_ln_bwd_args* a, m3p_stream_t str
 extern "C" int m3p_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int64_t n, m3p_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   M3P_REQUIRE(x && out, "m3p_colsum_bf16: null pointer");
-  M3P_REQUIRE(rows > 0 && n > 0 && n % 8 == 0 && ld % 8 == 0, "m3p_colsum_bf16: n and ld must be multiples of 8");
-  const ColGeom g = col_geom(rows, (int)n);
+  // n itself may be ragged (V = 250 002): the kernel reads whole 8-column vectors inside the row pitch and only adds
+  // the columns < n
+  M3P_REQUIRE(rows > 0 && n > 0 && ld % 8 == 0 && (n + 7) / 8 * 8 <= ld,
+              "m3p_colsum_bf16: ld must be a multiple of 8 and cover n rounded up to 8");
+  const ColGeom g = col_geom(rows, (int)((n + 7) / 8 * 8));
   colsum_kernel<<<dim3(g.stripes, g.row_blocks), EW_THREADS, (size_t)EW_THREADS * 8 * sizeof(float), stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ld, out, rows, (int)n, g.tx, g.rows_per_block);
   M3P_CUDA_OK(cudaGetLastError());

@@ -1195,9 +1195,7 @@ class _MlmFn(torch.autograd.Function):
             model._emb_dense_dirty = True
         ops.gemm(dlog, rows, V, d, n, model._proj_grad, a_mn=True, b_mn=True, out_f32=True, accumulate=True,
                  split_k=1, ldo=d)
-        ops.colsum(dlog, model._g("pred_layer.proj.bias"), rows=n, n=(V // 8) * 8)
-        if V % 8:
-            model._g("pred_layer.proj.bias")[(V // 8) * 8:] += dlog[:, (V // 8) * 8:V].float().sum(0)
+        ops.colsum(dlog, model._g("pred_layer.proj.bias"), rows=n, n=V)  # ragged V: whole vectors inside the pitch
         dt = None
         if ctx.needs_input_grad[0]:
             # d rows = dlogits E: a [n x d] output (12 tiles of 256 x 256 for n = 1024) with K = V = 250 002 — without a

@@ -120,6 +120,20 @@ def test_gemm_at_step_shapes(m3p, m, n, k):
         assert _rel(out2, ref.bfloat16()) < 1e-3, rep
 
 
+@pytest.mark.parametrize("rows,n,ld", [(1000, 1002, 1008), (37, 8, 8), (5000, 2304, 2304), (1024, 250002, 250008)])
+def test_colsum_ragged_columns(m3p, rows, n, ld):
+    """m3p_colsum_bf16: out[j] += sum_rows x[row][j] for j < n, n not necessarily a multiple of 8 (the MLM projection
+    bias, V = 250 002, inside logits padded to a pitch of 250 008): the padding columns must not leak into anything."""
+    from m3p_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(rows, ld, device="cuda", generator=g).bfloat16()
+    out = torch.full((ld,), 2.0, device="cuda")
+    ops.colsum(x, out, rows=rows, n=n, ld=ld)
+    want = x[:, :n].float().sum(0) + 2.0
+    assert float((out[:n] - want).abs().max()) < 1e-3 * max(float(want.abs().max()), 1.0)
+    assert bool((out[n:] == 2.0).all())
+
+
 def test_gemm_split_k_accumulates_fp32(m3p):
     from m3p_b200 import ops
     rows, n, k = 1000, 256, 128
