@@ -153,7 +153,9 @@ def _attn_ref(qkv, seqlen, B, S, H, scale):
 
 
 @pytest.mark.parametrize("B,S,H,ragged", [(2, 20, 2, False), (2, 128, 2, True), (3, 228, 2, True), (2, 256, 1, True),
-                                          (1, 129, 3, False), (4, 1, 1, False)])
+                                          (1, 129, 3, False), (4, 1, 1, False),
+                                          (40, 228, 12, True), (13, 130, 12, True)])  # > 148 (sequence, head) items: the
+                                          # persistent forward walks several items per SM (buffer / barrier-phase reuse)
 def test_attention_forward_backward(m3p, B, S, H, ragged):
     from m3p_b200 import ops
     torch.manual_seed(0)
