@@ -191,7 +191,10 @@ __device__ __forceinline__ void ln_residual16(float* x, const float* sgamma, con
   }
 }
 
-template <int EPI>
+// EVEN_E0: the caller guarantees an even element index e0 (true on the TMA path, whose 16-byte pitch rule makes N a
+// multiple of 4): the per-element fallback of the dropout generator is then not even compiled — the epilogue of the fp32
+// residual GEMM was 139 KB of SASS and lost a third of its issue slots to instruction fetch (ncu: stall_no_inst 33 %).
+template <int EPI, bool EVEN_E0 = false>
 __device__ __forceinline__ void epilogue_math(const GemmKernelParams& p, const uint32_t* acc, const float* sbias,
                                               const float* x, uint32_t e0, uint32_t seed_lo, uint32_t seed_hi,
                                               float* v, float* gq) {
@@ -205,7 +208,7 @@ __device__ __forceinline__ void epilogue_math(const GemmKernelParams& p, const u
   }
   if constexpr (EPI == M3P_EPI_DROP_RES) {
     if (p.thr16 != 0) {
-      if ((e0 & 1u) == 0) {
+      if (EVEN_E0 || (e0 & 1u) == 0) {
 #pragma unroll
         for (int j = 0; j < EW / 2; ++j) {
           const uint32_t h = drop_hash((e0 >> 1) + j, seed_lo, seed_hi);
@@ -632,9 +635,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t acc[2][EW];
       tmem_ld_32x32b_x16(t_base + cbase, acc[0]);
       if (use_tma) {
+        // GU groups per loop trip: just enough unrolling to keep the accumulator double-buffer index static
+        // (fully unrolled, the eight-group body no longer fitted the instruction cache)
+        constexpr int GU = (CPG & 1) ? 2 : 1;
+#pragma unroll 1
+        for (int gb = 0; gb < ng; gb += GU) {
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          if (g >= ng) break;  // half-width tile
+        for (int gu = 0; gu < GU; ++gu) {
+          const int g = gb + gu;
+          if (g >= ng) break;  // (ng is a multiple of GU; kept for safety)
           const int b = gg % RING;
           const int gcol0 = n0 + cbase + g * GWC;
           const bool valid = gcol0 < p.N && row0 < p.M;
@@ -653,7 +662,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
 #pragma unroll
           for (int ci = 0; ci < CPG; ++ci) {
-            const int i = g * CPG + ci, ii = i & 1;
+            const int i = g * CPG + ci;
+            const int ii = (gu * CPG + ci) & 1;  // == i & 1: gb * CPG is even
             tmem_ld_wait16(acc[ii]);
             if (i + 1 < nch) tmem_ld_32x32b_x16(t_base + cbase + (i + 1) * EW, acc[ii ^ 1]);
             float v[EW], gq[EW], x[EW];
@@ -665,7 +675,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
             const uint32_t e0 = static_cast<uint32_t>(row) * static_cast<uint32_t>(p.N) +
                                 static_cast<uint32_t>(gcol0 + ci * EW);
-            epilogue_math<EPI>(p, acc[ii], sbias + i * EW, x, e0, seed_lo, seed_hi, v, gq);
+            epilogue_math<EPI, true>(p, acc[ii], sbias + i * EW, x, e0, seed_lo, seed_hi, v, gq);
             if constexpr (F32R) stage_f32x16(slot, lane, v);
             else stage_bf16x16(slot, lane, ci, v);  // in place over the aux values this thread just consumed
             if constexpr (EPI == M3P_EPI_GELU) stage_bf16x16(slot + STG_TILE, lane, ci, gq);
@@ -709,6 +719,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (gg >= NG && gg < 2 * NG) GT_MARK();  // epi (2nd tile): store issued, next aux requested
 #endif
           ++gg;
+        }
         }
       } else {
 #pragma unroll 1
