@@ -6,11 +6,14 @@
 //   warp 0   TMA producer: cp.async.bulk.tensor tiles into a STAGES-deep 128B-swizzled smem ring
 //   warp 1   MMA issuer  : one elected thread issues tcgen05.mma (128 x BN x 16) and commits
 //   warp 2   TMEM allocator (2 accumulator stages of BN fp32 columns)
-//   warps 4-11 epilogue  : tcgen05.ld 32 columns at a time, fused math, vectorised global stores;
-//                          two warps per TMEM lane quarter, each taking half of the tile's columns
-//                          (the erf-GELU / dropout epilogues are issue-bound with one warp per quarter)
+//   warps 4-11 epilogue  : tcgen05.ld 16 columns at a time (the next chunk in flight), fused math, results staged
+//                          in per-warp swizzled shared-memory tiles and written by TMA bulk stores (aux operands
+//                          arrive the same way, two staging groups ahead); two warps per TMEM lane quarter, each
+//                          taking half of the tile's columns.  The staging-group loop is NOT fully unrolled: the
+//                          epilogue has to stay inside the instruction cache (see epilogue_math).
 // Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), and the
-// static persistent tile loop, so the epilogue of tile i overlaps the main loop of tile i+1.
+// static persistent tile loop, so the epilogue of tile i overlaps the main loop of tile i+1.  The last partial wave
+// of tiles may be issued as half-width units (GemmKernelParams::wide_units).
 //
 // Operand layouts: either operand may be K-major (reduction dim contiguous: forward "TN" GEMMs)
 // or MN-major (output dim contiguous: dgrad uses an MN-major B, wgrad MN-major A and B), so no
